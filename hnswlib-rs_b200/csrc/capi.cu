@@ -1,0 +1,373 @@
+// extern "C" surface of libhnsw_b200.so: the reference's libext.rs symbols (f32) + extensions.
+// Declarations and the reference file:line each one replaces are in include/hnsw_b200.h.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hnsw_b200.h"
+#include "index.h"
+
+using hb::Index;
+using hb::NeighbourOut;
+
+struct HnswApif32 {
+  Index* ix;
+};
+
+static thread_local std::string g_err;
+static int g_device = 0;
+
+static_assert(sizeof(Neighbour_api) == 16, "Neighbour_api must match #[repr(C)] {usize, f32}");
+static_assert(sizeof(NeighbourOut) == sizeof(Neighbour_api), "device answer slot must alias Neighbour_api");
+static_assert(sizeof(Neighbourhood_api) == 16 && sizeof(Vec_api_Neighbourhood_api) == 16, "libext.rs struct layouts");
+
+static int set_err(const std::string& m) {
+  g_err = m;
+  return -1;
+}
+static int pass(Index* ix, int r) {
+  if (r) g_err = ix->err();
+  return r;
+}
+
+static int metric_from_name(const uint8_t* name, size_t len) {
+  std::string s((const char*)name, len);
+  if (s == "DistL1") return hb::METRIC_L1;
+  if (s == "DistL2") return hb::METRIC_L2;
+  if (s == "DistDot") return hb::METRIC_DOT;
+  if (s == "DistCosine") return hb::METRIC_COSINE;
+  if (s == "DistHellinger") return hb::METRIC_HELLINGER;
+  if (s == "DistJeffreys") return hb::METRIC_JEFFREYS;
+  if (s == "DistJensenShannon") return hb::METRIC_JENSENSHANNON;
+  return -1;
+}
+
+static const HnswApif32* make_index(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname,
+                                    size_t max_elements, size_t max_layer) {
+  if (!cdistname) {
+    set_err("distance name is NULL");
+    return nullptr;
+  }
+  const int metric = metric_from_name(cdistname, namelen);
+  if (metric < 0) {  // libext.rs:520-523: unknown distance => null
+    set_err("unknown distance name '" + std::string((const char*)cdistname, namelen) + "'");
+    return nullptr;
+  }
+  if (max_nb_conn < 2 || max_nb_conn > 256) {  // hnsw.rs:784-787 caps at 256; ln(1) = 0 breaks the level law
+    set_err("max_nb_connection must be in [2, 256]");
+    return nullptr;
+  }
+  if (ef_const == 0 || max_layer == 0) {
+    set_err("ef_construction and max_layer must be positive");
+    return nullptr;
+  }
+  Index* ix = new Index((int)max_nb_conn, max_elements, (int)max_layer, (int)ef_const, metric, g_device);
+  if (!ix->ok()) {
+    set_err(ix->err());
+    delete ix;
+    return nullptr;
+  }
+  return new HnswApif32{ix};
+}
+
+extern "C" {
+
+const HnswApif32* init_hnsw_f32(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname) {
+  return make_index(max_nb_conn, ef_const, namelen, cdistname, 10000, 16);  // libext.rs:470-518
+}
+
+const HnswApif32* new_hnsw_f32(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname,
+                               size_t max_elements, size_t max_layer) {
+  return make_index(max_nb_conn, ef_const, namelen, cdistname, max_elements, max_layer);
+}
+
+void drop_hnsw_f32(const HnswApif32* p) {
+  if (!p) return;
+  delete p->ix;
+  delete p;
+}
+
+const HnswApif32* init_hnsw_ptrdist_f32(size_t, size_t, float (*)(const float*, const float*, unsigned long long)) {
+  set_err("init_hnsw_ptrdist_f32: a host distance callback cannot run inside a CUDA kernel; use a named distance");
+  return nullptr;
+}
+
+void insert_f32(HnswApif32* h, size_t len, const float* data, size_t id) {
+  if (!h || !data) {
+    set_err("insert_f32: NULL argument");
+    return;
+  }
+  std::lock_guard<std::mutex> g(h->ix->mu);
+  if (pass(h->ix, h->ix->set_dim((int)len))) return;
+  uint64_t id64 = id;
+  pass(h->ix, h->ix->insert_batch(data, 1, len, nullptr, &id64, nullptr));
+}
+
+void parallel_insert_f32(HnswApif32* h, size_t nb_vec, size_t vec_len, const float** datas, const size_t* ids) {
+  if (!h || !datas || !ids) {
+    set_err("parallel_insert_f32: NULL argument");
+    return;
+  }
+  std::lock_guard<std::mutex> g(h->ix->mu);
+  if (pass(h->ix, h->ix->set_dim((int)vec_len))) return;
+  std::vector<uint64_t> id64(ids, ids + nb_vec);
+  pass(h->ix, h->ix->insert_batch(nullptr, nb_vec, vec_len, datas, id64.data(), nullptr));
+}
+
+const Neighbourhood_api* search_neighbours_f32(const HnswApif32* h, size_t len, const float* data, size_t knbn,
+                                               size_t ef_search) {
+  if (!h || !data || knbn == 0) {
+    set_err("search_neighbours_f32: bad argument");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> g(h->ix->mu);
+  Neighbour_api* nb = (Neighbour_api*)malloc(sizeof(Neighbour_api) * knbn);
+  int32_t cnt = 0;
+  if (pass(h->ix, h->ix->search_host(data, nullptr, 1, (int)len, knbn, ef_search, nullptr, (NeighbourOut*)nb, &cnt))) {
+    free(nb);
+    return nullptr;
+  }
+  Neighbourhood_api* out = (Neighbourhood_api*)malloc(sizeof(Neighbourhood_api));
+  out->nbgh = cnt;
+  out->neighbours = nb;
+  return out;
+}
+
+struct VecApiBox {
+  Vec_api_Neighbourhood_api v;  // first member: the pointer handed to the caller
+  Neighbourhood_api* hoods;
+  Neighbour_api* block;
+};
+
+const Vec_api_Neighbourhood_api* parallel_search_neighbours_f32(const HnswApif32* h, size_t nb_vec, int64_t vec_len,
+                                                                const float** data, size_t knbn, size_t ef_search) {
+  if (!h || (!data && nb_vec) || knbn == 0) {
+    set_err("parallel_search_neighbours_f32: bad argument");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> g(h->ix->mu);
+  VecApiBox* box = (VecApiBox*)malloc(sizeof(VecApiBox));
+  box->hoods = (Neighbourhood_api*)malloc(sizeof(Neighbourhood_api) * (nb_vec ? nb_vec : 1));
+  box->block = (Neighbour_api*)malloc(sizeof(Neighbour_api) * (nb_vec ? nb_vec * knbn : 1));
+  std::vector<int32_t> cnt(nb_vec);
+  if (pass(h->ix, h->ix->search_host(nullptr, data, nb_vec, (int)vec_len, knbn, ef_search, nullptr,
+                                     (NeighbourOut*)box->block, cnt.data()))) {
+    free(box->hoods);
+    free(box->block);
+    free(box);
+    return nullptr;
+  }
+  for (size_t i = 0; i < nb_vec; ++i) {  // input order, hnsw.rs:1622-1633
+    box->hoods[i].nbgh = cnt[i];
+    box->hoods[i].neighbours = box->block + i * knbn;
+  }
+  box->v.len = (int64_t)nb_vec;
+  box->v.ptr = box->hoods;
+  return &box->v;
+}
+
+int64_t file_dump_f32(const HnswApif32* h, size_t, const uint8_t*) {
+  (void)h;
+  set_err("file_dump_f32: the .hnsw.graph/.hnsw.data writer is SURVEY §8 row f2 (next), not built yet");
+  return -1;
+}
+
+void init_rust_log(void) {}
+
+// ------------------------------------------------------------------ extensions
+const char* hnsw_b200_last_error(void) { return g_err.c_str(); }
+
+int hnsw_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int hnsw_b200_set_device(int device) {
+  int n = hnsw_b200_device_count();
+  if (device < 0 || device >= n) return set_err("device index out of range");
+  g_device = device;
+  return 0;
+}
+
+void hnsw_b200_free_neighbourhood(const Neighbourhood_api* p) {
+  if (!p) return;
+  free((void*)p->neighbours);
+  free((void*)p);
+}
+
+void hnsw_b200_free_vec_api(const Vec_api_Neighbourhood_api* p) {
+  if (!p) return;
+  VecApiBox* box = (VecApiBox*)p;
+  free(box->hoods);
+  free(box->block);
+  free(box);
+}
+
+#define HB_H(h) \
+  if (!(h)) return set_err("NULL handle"); \
+  Index* ix = (h)->ix;                     \
+  std::lock_guard<std::mutex> g__(ix->mu)
+
+int hnsw_b200_set_extend_candidates(HnswApif32* h, int flag) {
+  HB_H(h);
+  if (flag) return set_err("extend_candidates is not supported by the GPU insert path yet");
+  ix->extend_candidates = false;
+  return 0;
+}
+int hnsw_b200_set_keeping_pruned(HnswApif32* h, int flag) {
+  HB_H(h);
+  ix->keep_pruned = flag != 0;
+  return 0;
+}
+int hnsw_b200_modify_level_scale(HnswApif32* h, double scale) {
+  HB_H(h);
+  if (ix->n > 0) return set_err("modify_level_scale: index already holds points (hnsw.rs:881-888)");
+  if (!(scale >= 0.2 && scale <= 1.0)) return set_err("modify_level_scale: factor must be in [0.2, 1]");  // hnsw.rs:889-900
+  ix->level_scale = scale / std::log((double)ix->M);
+  return 0;
+}
+int hnsw_b200_set_searching_mode(HnswApif32* h, int flag) {
+  HB_H(h);
+  ix->searching = flag != 0;
+  return 0;
+}
+int hnsw_b200_set_level_seed(HnswApif32* h, uint64_t seed) {
+  HB_H(h);
+  ix->rng.s = seed;
+  return 0;
+}
+uint64_t hnsw_b200_get_nb_point(const HnswApif32* h) { return h ? h->ix->n : 0; }
+int hnsw_b200_get_max_level_observed(const HnswApif32* h) { return h ? std::max(h->ix->entry_level, 0) : 0; }
+int hnsw_b200_get_dim(const HnswApif32* h) { return h ? h->ix->dim : 0; }
+int hnsw_b200_set_insert_batching(HnswApif32* h, uint32_t ratio, uint32_t max_batch) {
+  HB_H(h);
+  if (ratio == 0 || max_batch == 0) return set_err("ratio and max_batch must be positive");
+  ix->batch_ratio = ratio;
+  ix->batch_max = max_batch;
+  return 0;
+}
+
+int hnsw_b200_insert_flat(HnswApif32* h, const float* vecs, uint64_t n, uint64_t dim, const uint64_t* ids,
+                          const int32_t* levels) {
+  HB_H(h);
+  if (n == 0) return 0;
+  if (!vecs) return set_err("vecs is NULL");
+  int r;
+  if ((r = pass(ix, ix->set_dim((int)dim)))) return r;
+  return pass(ix, ix->insert_batch(vecs, n, dim, nullptr, ids, levels));
+}
+
+int hnsw_b200_search_flat(const HnswApif32* h, const float* queries, uint64_t nq, uint64_t dim, uint64_t knbn,
+                          uint64_t ef_search, int filter_mode, const uint64_t* filter_ids, uint64_t nfilter,
+                          hnsw_b200_filter_fn fn, void* ctx, uint64_t* out_ids, float* out_dist,
+                          uint32_t* out_internal, int32_t* out_pid, int32_t* out_counts) {
+  HB_H(h);
+  if (nq == 0) return 0;
+  if (!queries || !out_ids || !out_dist || !out_counts || knbn == 0) return set_err("bad argument");
+  std::vector<uint32_t> bits;
+  const uint32_t* fb = nullptr;
+  if (filter_mode) {
+    int r = pass(ix, ix->make_filter_bits(filter_mode, filter_ids, nfilter, fn, ctx, bits));
+    if (r) return r;
+    fb = bits.data();
+  }
+  std::vector<NeighbourOut> tmp(nq * knbn);
+  int r = pass(ix, ix->search_host(queries, nullptr, nq, (int)dim, knbn, ef_search, fb, tmp.data(), out_counts));
+  if (r) return r;
+  for (uint64_t i = 0; i < nq; ++i)
+    for (uint64_t j = 0; j < knbn; ++j) {
+      const uint64_t o = i * knbn + j;
+      const bool valid = (int64_t)j < out_counts[i];
+      out_ids[o] = valid ? tmp[o].origin : ~0ull;
+      out_dist[o] = valid ? tmp[o].dist : __builtin_inff();
+      if (out_internal) out_internal[o] = valid ? tmp[o].internal : hb::INVALID_ID;
+      if (out_pid) {  // PointId(level, rank), hnsw.rs:46
+        out_pid[2 * o] = valid ? (int32_t)ix->h_level[tmp[o].internal] : -1;
+        out_pid[2 * o + 1] = valid ? ix->h_rank[tmp[o].internal] : -1;
+      }
+    }
+  return 0;
+}
+
+int hnsw_b200_search_device(const HnswApif32* h, const float* d_queries, uint64_t nq, uint64_t knbn,
+                            uint64_t ef_search, void* d_out, int32_t* d_counts, int sync, float* kernel_ms) {
+  HB_H(h);
+  return pass(ix, ix->search_device(d_queries, nq, knbn, ef_search, nullptr, (NeighbourOut*)d_out, d_counts, sync != 0,
+                                    kernel_ms));
+}
+
+int hnsw_b200_enable_stats(HnswApif32* h, int enable) {
+  HB_H(h);
+  return ix->enable_stats(enable != 0);
+}
+int hnsw_b200_get_stats(const HnswApif32* h, uint64_t* out4, int reset) {
+  HB_H(h);
+  return pass(ix, ix->get_stats(out4, reset != 0));
+}
+
+int hnsw_b200_export_points(const HnswApif32* h, uint8_t* levels, int32_t* ranks, uint64_t* origin, int64_t* entry) {
+  HB_H(h);
+  for (size_t i = 0; i < ix->n; ++i) {
+    if (levels) levels[i] = ix->h_level[i];
+    if (ranks) ranks[i] = ix->h_rank[i];
+    if (origin) origin[i] = ix->h_origin[i];
+  }
+  if (entry) *entry = ix->entry == hb::INVALID_ID ? -1 : (int64_t)ix->entry;
+  return 0;
+}
+int hnsw_b200_export_vectors(const HnswApif32* h, float* out) {
+  HB_H(h);
+  return pass(ix, ix->export_vectors(out));
+}
+int64_t hnsw_b200_layer_edges(const HnswApif32* h, int layer) {
+  if (!h) return set_err("NULL handle");
+  Index* ix = h->ix;
+  std::lock_guard<std::mutex> g(ix->mu);
+  int64_t total = 0;
+  if (pass(ix, ix->export_layer(layer, nullptr, nullptr, nullptr, &total))) return -1;
+  return total;
+}
+int hnsw_b200_export_layer(const HnswApif32* h, int layer, uint64_t* offsets, uint32_t* ids, float* dists) {
+  HB_H(h);
+  return pass(ix, ix->export_layer(layer, offsets, ids, dists, nullptr));
+}
+int hnsw_b200_import_graph(HnswApif32* h, const float* vecs, uint64_t n, uint64_t dim, const uint64_t* origin,
+                           const uint8_t* levels, int64_t entry, int nlayers, const uint64_t* const* offsets,
+                           const uint32_t* const* ids, const float* const* dists) {
+  HB_H(h);
+  return pass(ix, ix->import_graph(vecs, n, (int)dim, origin, levels, entry, nlayers, offsets, ids, dists));
+}
+
+int hnsw_b200_blob_header(const HnswApif32* h, uint64_t* header16) {
+  HB_H(h);
+  return ix->blob_header(header16);
+}
+int hnsw_b200_blob_alloc(HnswApif32* h, const uint64_t* header16) {
+  HB_H(h);
+  return pass(ix, ix->blob_alloc(header16));
+}
+int hnsw_b200_blob_count(const HnswApif32* h) { return h ? h->ix->blob_count() : 0; }
+int hnsw_b200_blob_info(const HnswApif32* h, int i, void** dev_ptr, uint64_t* nbytes) {
+  HB_H(h);
+  return pass(ix, ix->blob_info(i, dev_ptr, nbytes));
+}
+int hnsw_b200_blob_commit(HnswApif32* h) {
+  HB_H(h);
+  return pass(ix, ix->blob_commit());
+}
+
+int hnsw_b200_dist_batch(const HnswApif32* h, const float* queries, uint64_t nq, uint64_t dim, const uint32_t* cand,
+                         uint64_t m, float* out) {
+  HB_H(h);
+  return pass(ix, ix->dist_batch(queries, nq, (int)dim, cand, m, out));
+}
+int hnsw_b200_bruteforce(const HnswApif32* h, const float* queries, uint64_t nq, uint64_t dim, uint64_t k,
+                         uint32_t* out_ids, float* out_dist) {
+  HB_H(h);
+  return pass(ix, ix->bruteforce(queries, nq, (int)dim, k, out_ids, out_dist));
+}
+
+}  // extern "C"

@@ -1,0 +1,383 @@
+// Device-side building blocks of the B200 HNSW engine (sm_100a).
+//
+// Replaces, on the hot path of jean-pierreBoth/hnswlib-rs:
+//   Point / PointWithOrder / PointIndexation pointer graph  (/root/reference/src/hnsw.rs:164-173,265-271,395-408)
+//     -> GraphView: flat 128B-aligned point store + fixed-stride adjacency in HBM
+//   Distance<T>::eval (crate anndists; call sites hnsw.rs:952,1026,1506,1518)
+//     -> warp_dists<>: 8 lanes per row, float4 loads, xor-butterfly reduce
+//   hashbrown visited map (hnsw.rs:955-956,1016-1017)  -> Visited: per-warp epoch-tagged open-addressing table
+//   std BinaryHeap W and C (hnsw.rs:940-1053)           -> SortedQueue: one sorted array of (dist,id,expanded) keys
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hb {
+
+constexpr uint32_t INVALID_ID = 0xFFFFFFFFu;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int MAX_LAYERS = 16;  // NB_LAYER_MAX, hnsw.rs:42
+
+enum Metric : int {
+  METRIC_L1 = 0,
+  METRIC_L2 = 1,
+  METRIC_DOT = 2,
+  METRIC_COSINE = 3,
+  METRIC_HAMMING = 4,
+  METRIC_JACCARD = 5,
+  METRIC_HELLINGER = 6,
+  METRIC_JEFFREYS = 7,
+  METRIC_JENSENSHANNON = 8,
+};
+
+// ------------------------------------------------------------------------------------------------
+// HBM layout of the index.  Internal id = insertion rank.  Rows of `vec` are d_pad floats
+// (d rounded up to 32 floats = 128 B, zero padded) so that a row is a whole number of cache lines
+// and 8 lanes x float4 cover exactly one line.
+// Layer 0 adjacency: adj0[id][deg0] (deg0 = 2*max_nb_connection), INVALID_ID-terminated, with the
+// distance-to-owner of each link in adj0_d (needed by the insert path only).
+// Layers >= 1: a point owns `plevel[id]` consecutive lists of M slots starting at list index
+// up_off[id] in adjU (list for layer l is up_off[id] + l - 1).  plevel >= level; it exceeds the
+// point's own level only for former entry points (see DESIGN.md "lists above a point's level").
+struct GraphView {
+  const float* vec;
+  int d4;  // float4 per row = d_pad / 4 (multiple of 8)
+  uint32_t* adj0;
+  float* adj0_d;
+  int deg0;
+  uint32_t* adjU;
+  float* adjU_d;
+  int M;
+  const uint32_t* up_off;
+  const uint8_t* plevel;
+  const uint8_t* level;
+  const uint64_t* origin;
+  uint32_t n;
+  uint32_t entry;  // INVALID_ID when empty
+  int entry_level;
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// list of (p, layer): returns pointer to ids (or nullptr when the point owns no list there) and capacity
+__device__ __forceinline__ const uint32_t* list_ids(const GraphView& g, uint32_t p, int layer, int& cap) {
+  if (layer == 0) {
+    cap = g.deg0;
+    return g.adj0 + (size_t)p * g.deg0;
+  }
+  if (layer > (int)g.plevel[p]) {
+    cap = 0;
+    return nullptr;
+  }
+  cap = g.M;
+  return g.adjU + ((size_t)g.up_off[p] + (layer - 1)) * g.M;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Distance functors.  BIT-EXACT SUMMATION ORDER (mirrored by oracle/distances.h accumulate_gpu):
+// lane g (0..7) of a row group owns float4 chunks g, g+8, g+16, ...; inside a chunk x,y,z,w in that
+// order; fused multiply-add where a product is accumulated; then partials are combined with a
+// 4,2,1 xor butterfly and finished (sqrt / 1-x / ...).  Zero padding adds exact zeros.
+struct OpL2 {
+  typedef float acc_t;
+  static __device__ __forceinline__ acc_t zero() { return 0.f; }
+  static __device__ __forceinline__ void step(acc_t& a, float q, float x) {
+    float df = __fsub_rn(q, x);
+    a = __fmaf_rn(df, df, a);
+  }
+  static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
+  static __device__ __forceinline__ float finish(acc_t a) { return __fsqrt_rn(a); }
+};
+struct OpL1 {
+  typedef float acc_t;
+  static __device__ __forceinline__ acc_t zero() { return 0.f; }
+  static __device__ __forceinline__ void step(acc_t& a, float q, float x) { a = __fadd_rn(a, fabsf(__fsub_rn(q, x))); }
+  static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
+  static __device__ __forceinline__ float finish(acc_t a) { return a; }
+};
+struct OpDot {
+  typedef float acc_t;
+  static __device__ __forceinline__ acc_t zero() { return 0.f; }
+  static __device__ __forceinline__ void step(acc_t& a, float q, float x) { a = __fmaf_rn(q, x, a); }
+  static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
+  static __device__ __forceinline__ float finish(acc_t a) { return fmaxf(__fsub_rn(1.0f, a), 0.f); }
+};
+struct Cos3 {
+  double ab, aa, bb;
+};
+struct OpCosine {  // f64 accumulation like anndists DistCosine
+  typedef Cos3 acc_t;
+  static __device__ __forceinline__ acc_t zero() { return Cos3{0., 0., 0.}; }
+  static __device__ __forceinline__ void step(acc_t& a, float q, float x) {
+    double dq = (double)q, dx = (double)x;
+    a.ab = __fma_rn(dq, dx, a.ab);
+    a.aa = __fma_rn(dq, dq, a.aa);
+    a.bb = __fma_rn(dx, dx, a.bb);
+  }
+  static __device__ __forceinline__ acc_t comb(acc_t a, int off) {
+    Cos3 r;
+    r.ab = __dadd_rn(a.ab, __shfl_xor_sync(FULL, a.ab, off));
+    r.aa = __dadd_rn(a.aa, __shfl_xor_sync(FULL, a.aa, off));
+    r.bb = __dadd_rn(a.bb, __shfl_xor_sync(FULL, a.bb, off));
+    return r;
+  }
+  static __device__ __forceinline__ float finish(acc_t a) {
+    if (a.aa > 0. && a.bb > 0.) {
+      double r = __dsub_rn(1., __ddiv_rn(a.ab, __dsqrt_rn(__dmul_rn(a.aa, a.bb))));
+      return (float)(r > 0. ? r : 0.);
+    }
+    return 0.f;
+  }
+};
+struct OpHellinger {
+  typedef float acc_t;
+  static __device__ __forceinline__ acc_t zero() { return 0.f; }
+  static __device__ __forceinline__ void step(acc_t& a, float q, float x) { a = __fadd_rn(a, __fsqrt_rn(__fmul_rn(q, x))); }
+  static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
+  static __device__ __forceinline__ float finish(acc_t a) { return __fsqrt_rn(fmaxf(__fsub_rn(1.0f, a), 0.f)); }
+};
+struct OpJeffreys {
+  typedef float acc_t;
+  static __device__ __forceinline__ acc_t zero() { return 0.f; }
+  static __device__ __forceinline__ void step(acc_t& a, float q, float x) {
+    float qm = fmaxf(q, 1e-30f), xm = fmaxf(x, 1e-30f);
+    a = __fadd_rn(a, __fmul_rn(__fsub_rn(q, x), logf(__fdiv_rn(qm, xm))));
+  }
+  static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
+  static __device__ __forceinline__ float finish(acc_t a) { return a; }
+};
+struct OpJS {
+  typedef float acc_t;
+  static __device__ __forceinline__ acc_t zero() { return 0.f; }
+  static __device__ __forceinline__ void step(acc_t& a, float q, float x) {
+    float m = __fmul_rn(0.5f, __fadd_rn(q, x));
+    float t = 0.f;
+    if (q > 0.f) t = __fadd_rn(t, __fmul_rn(q, logf(__fdiv_rn(q, m))));
+    if (x > 0.f) t = __fadd_rn(t, __fmul_rn(x, logf(__fdiv_rn(x, m))));
+    a = __fadd_rn(a, t);
+  }
+  static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
+  static __device__ __forceinline__ float finish(acc_t a) { return __fsqrt_rn(fmaxf(__fmul_rn(0.5f, a), 0.f)); }
+};
+
+template <class Op>
+__device__ __forceinline__ void step4(typename Op::acc_t& a, const float4& q, const float4& x) {
+  Op::step(a, q.x, x.x);
+  Op::step(a, q.y, x.y);
+  Op::step(a, q.z, x.z);
+  Op::step(a, q.w, x.w);
+}
+
+template <class Op>
+__device__ __forceinline__ float reduce8(typename Op::acc_t a) {
+  a = Op::comb(a, 4);
+  a = Op::comb(a, 2);
+  a = Op::comb(a, 1);
+  return Op::finish(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp_dists: distances from the query (float4 view in shared memory, d4 chunks) to `n` rows named
+// by ids[] (shared memory), results to out[] (shared memory).  8 lanes per row, 4 rows per pass,
+// U passes in flight; CH = d4/8 when known at compile time (CH float4 loads per lane per row),
+// CH = 0 for the generic loop.  Every load instruction covers 4 rows x 128 B contiguous.
+template <class Op, int CH, int U>
+__device__ __forceinline__ void warp_dists(const float4* __restrict__ vec, int d4, const float4* q4, const uint32_t* ids,
+                                           int n, float* out) {
+  const int lane = lane_id();
+  const int g = lane & 7, r = lane >> 3;
+  if constexpr (CH > 0) {
+    float4 qv[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) qv[i] = q4[g + 8 * i];
+    for (int base = 0; base < n; base += 4 * U) {
+      const float4* row[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        int idx = base + u * 4 + r;
+        uint32_t id = ids[idx < n ? idx : n - 1];
+        row[u] = vec + (size_t)id * d4 + g;
+      }
+      float4 x[U][CH];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int i = 0; i < CH; ++i) x[u][i] = __ldg(row[u] + 8 * i);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        typename Op::acc_t a = Op::zero();
+#pragma unroll
+        for (int i = 0; i < CH; ++i) step4<Op>(a, qv[i], x[u][i]);
+        float dist = reduce8<Op>(a);
+        int idx = base + u * 4 + r;
+        if (g == 0 && idx < n) out[idx] = dist;
+      }
+    }
+  } else {
+    const int nch = d4 >> 3;
+    for (int base = 0; base < n; base += 4 * U) {
+      const float4* row[U];
+      typename Op::acc_t a[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        int idx = base + u * 4 + r;
+        uint32_t id = ids[idx < n ? idx : n - 1];
+        row[u] = vec + (size_t)id * d4 + g;
+        a[u] = Op::zero();
+      }
+#pragma unroll 4
+      for (int i = 0; i < nch; ++i) {
+        float4 qv = q4[g + 8 * i];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float4 x = __ldg(row[u] + 8 * i);
+          step4<Op>(a[u], qv, x);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float dist = reduce8<Op>(a[u]);
+        int idx = base + u * 4 + r;
+        if (g == 0 && idx < n) out[idx] = dist;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Visited set: one open-addressing table per resident warp ("warp slot") in global memory (L2
+// resident).  Entry = (epoch << id_bits) | id; an entry whose epoch differs from the current one is
+// free, so a new search only bumps the epoch instead of clearing.  Exact (no false positives).
+struct VisitedCfg {
+  uint32_t* tables;   // [n_slots][cap]
+  uint32_t* epochs;   // [n_slots] persisted across launches
+  uint32_t cap;       // power of two
+  int shift;          // 32 - log2(cap)
+  int id_bits;        // bits needed for ids
+};
+
+struct Visited {
+  uint32_t* tab;
+  uint32_t mask;
+  int shift;
+  int id_bits;
+  uint32_t epoch;
+  uint32_t epoch_max;
+  uint32_t tag;
+  uint32_t used;  // lane-local count of insertions (summed on demand)
+  uint32_t limit;
+
+  __device__ __forceinline__ void init(const VisitedCfg& c, uint32_t slot) {
+    tab = c.tables + (size_t)slot * c.cap;
+    mask = c.cap - 1;
+    shift = c.shift;
+    id_bits = c.id_bits;
+    epoch_max = (id_bits >= 32) ? 0u : ((1u << (32 - id_bits)) - 1u);
+    epoch = c.epochs[slot];
+    limit = c.cap - (c.cap >> 2);
+    used = 0;
+  }
+  __device__ __forceinline__ void save(const VisitedCfg& c, uint32_t slot) {
+    if (lane_id() == 0) c.epochs[slot] = epoch;
+  }
+  // start a new search: all lanes call
+  __device__ __forceinline__ void begin() {
+    if (epoch >= epoch_max) {
+      for (uint32_t i = lane_id(); i <= mask; i += 32) tab[i] = 0u;
+      __syncwarp();
+      epoch = 0;
+    }
+    epoch += 1;
+    tag = epoch << id_bits;
+    used = 0;
+  }
+  // per-lane; true when id was not yet in the set (and is now)
+  __device__ __forceinline__ bool test_and_set(uint32_t id) {
+    const uint32_t want = tag | id;
+    uint32_t h = (id * 2654435761u) >> shift;
+    for (;;) {
+      uint32_t cur = __ldcg(tab + h);
+      if (cur == want) return false;
+      if ((cur >> id_bits) != epoch) {
+        uint32_t old = atomicCAS(tab + h, cur, want);
+        if (old == cur) {
+          used++;
+          return true;
+        }
+        if (old == want) return false;
+      }
+      h = (h + 1) & mask;
+    }
+  }
+  __device__ __forceinline__ bool overflowing() const {
+    uint32_t t = used;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+    return t >= limit;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Queue keys: (float bits of distance << 32) | (id << 1) | expanded.  Distances are >= 0 so the
+// unsigned order of the bits is the numeric order; ties on distance order by id: the total order
+// (dist, id) of the oracle's MODE_DET.
+__device__ __forceinline__ uint64_t make_key(float d, uint32_t id) {
+  return ((uint64_t)__float_as_uint(d) << 32) | ((uint64_t)id << 1);
+}
+__device__ __forceinline__ float key_dist(uint64_t k) { return __uint_as_float((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_id(uint64_t k) { return ((uint32_t)k) >> 1; }
+
+// One sorted array (ascending) in shared memory standing for both reference queues: W = the array,
+// C = its not-yet-expanded entries (entries evicted from W can never be expanded again, see
+// DESIGN.md "one array for W and C").  All functions are warp-collective.
+struct SortedQueue {
+  uint64_t* w;
+  int n;
+  int cap;  // ef
+
+  __device__ __forceinline__ void reset(uint64_t* buf, int ef) {
+    w = buf;
+    n = 0;
+    cap = ef;
+  }
+  // index of the nearest unexpanded entry, or -1
+  __device__ __forceinline__ int first_unexpanded() const {
+    const int lane = lane_id();
+    for (int base = 0; base < n; base += 32) {
+      int i = base + lane;
+      bool open = (i < n) && ((w[i] & 1ull) == 0ull);
+      unsigned m = __ballot_sync(FULL, open);
+      if (m) return base + __ffs(m) - 1;
+    }
+    return -1;
+  }
+  __device__ __forceinline__ bool accepts(uint64_t key) const { return n < cap || key < (w[n - 1] & ~1ull); }
+  // insert key (expanded bit clear) keeping order; drops the largest entry when full. Caller checked accepts().
+  __device__ __forceinline__ void insert(uint64_t key) {
+    const int lane = lane_id();
+    int pos = 0;
+    for (int base = 0; base < n; base += 32) {
+      int i = base + lane;
+      bool less = (i < n) && (w[i] < key);
+      pos += __popc(__ballot_sync(FULL, less));
+    }
+    const int new_n = n < cap ? n + 1 : cap;
+    // shift (pos, new_n-1] right by one; chunks are handled top-down so that a chunk's sources are
+    // read before a lower chunk overwrites them
+    int top = new_n - 1;
+    while (top > pos) {
+      int lo = top - 31 > pos + 1 ? top - 31 : pos + 1;  // chunk [lo, top]
+      int i = lo + lane;
+      uint64_t v = 0;
+      if (i <= top) v = w[i - 1];
+      __syncwarp();
+      if (i <= top) w[i] = v;
+      __syncwarp();
+      top = lo - 1;
+    }
+    if (lane == 0) w[pos] = key;
+    __syncwarp();
+    n = new_n;
+  }
+};
+
+}  // namespace hb

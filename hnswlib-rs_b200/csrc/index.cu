@@ -1,0 +1,758 @@
+// Host-side index: HBM allocation, insert-batch scheduling, query launches, import/export.
+// See index.h for what it replaces in the reference.
+#include "index.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace hb {
+
+#define HB_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+static size_t next_pow2(size_t x) {
+  size_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+static int ilog2(size_t p) {
+  int r = 0;
+  while (((size_t)1 << r) < p) ++r;
+  return r;
+}
+
+int Index::fail(const std::string& m) const {
+  err_ = m;
+  return -1;
+}
+int Index::cuda_fail(cudaError_t e, const char* what) const {
+  err_ = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
+  return -2;
+}
+
+Index::Index(int M_, size_t max_elements_, int max_layer_, int ef_c_, int metric_, int device_)
+    : M(M_), max_layer(std::min(max_layer_, MAX_LAYERS)), ef_c(ef_c_), metric(metric_), device(device_),
+      max_elements(max_elements_) {
+  for (int l = 0; l < MAX_LAYERS; ++l) layer_count[l] = 0;
+  level_scale = 1.0 / std::log((double)M);  // hnsw.rs:327
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    err_ = std::string("no usable CUDA device: ") + cudaGetErrorString(e) + " (this engine has no CPU fallback)";
+    return;
+  }
+  if (device >= ndev) {
+    err_ = "device index out of range";
+    return;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&ev0_)) != cudaSuccess || (e = cudaEventCreate(&ev1_)) != cudaSuccess) {
+    err_ = std::string("CUDA init failed: ") + cudaGetErrorString(e);
+    return;
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    err_ = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+    return;
+  }
+  sm_count_ = prop.multiProcessorCount;
+  if ((e = cudaMalloc(&d_counter_, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&d_status_, sizeof(int))) != cudaSuccess ||
+      (e = cudaMalloc(&d_stats_, 4 * sizeof(unsigned long long))) != cudaSuccess) {
+    err_ = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    return;
+  }
+  cudaMemset(d_stats_, 0, 4 * sizeof(unsigned long long));
+  cudaMemset(d_status_, 0, sizeof(int));
+  ok_ = true;
+}
+
+Index::~Index() {
+  if (stream_) cudaStreamSynchronize(stream_);
+  cudaFree(d_vec_.p); cudaFree(d_adj0_.p); cudaFree(d_adjU_.p); cudaFree(d_upoff_.p); cudaFree(d_adj0d_.p);
+  cudaFree(d_adjUd_.p); cudaFree(d_level_.p); cudaFree(d_plevel_.p); cudaFree(d_origin_.p); cudaFree(d_locks_.p);
+  cudaFree(d_vis_tab_); cudaFree(d_vis_epoch_); cudaFree(d_counter_); cudaFree(d_status_); cudaFree(d_stats_);
+  cudaFree(d_q_); cudaFree(d_out_); cudaFree(d_cnt_); cudaFree(d_fbits_); cudaFree(d_mask_);
+  if (h_pin_) cudaFreeHost(h_pin_);
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+template <class T>
+int Index::grow(DevArray<T>& a, size_t need, size_t keep, int fill) {
+  if (need <= a.cap) return 0;
+  T* np = nullptr;
+  HB_CUDA(cudaMalloc(&np, need * sizeof(T)));
+  HB_CUDA(cudaMemsetAsync(np, fill, need * sizeof(T), stream_));
+  if (keep && a.p) HB_CUDA(cudaMemcpyAsync(np, a.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+  HB_CUDA(cudaStreamSynchronize(stream_));
+  cudaFree(a.p);
+  a.p = np;
+  a.cap = need;
+  return 0;
+}
+
+int Index::set_dim(int d) {
+  if (d <= 0) return fail("dimension must be positive");
+  if (dim == 0) {
+    dim = d;
+    d_pad = (d + 31) / 32 * 32;
+    return 0;
+  }
+  if (dim != d) return fail("vector length differs from the index dimension (the flat point store needs one dimension)");
+  return 0;
+}
+
+int Index::ensure_points(size_t need) {
+  if (need <= cap_) return 0;
+  if (need >= (size_t)1 << 31) return fail("more than 2^31 points are not supported");
+  size_t nc = std::max(need, cap_ * 2);
+  if (cap_ == 0) nc = std::max(nc, std::max<size_t>(max_elements, 1024));
+  const size_t deg0 = (size_t)2 * M;
+  int r;
+  if ((r = grow(d_vec_, nc * d_pad, n * d_pad, 0))) return r;
+  if ((r = grow(d_adj0_, nc * deg0, n * deg0, 0xFF))) return r;
+  if ((r = grow(d_adj0d_, nc * deg0, n * deg0, 0))) return r;
+  if ((r = grow(d_upoff_, nc, n, 0xFF))) return r;
+  if ((r = grow(d_level_, nc, n, 0))) return r;
+  if ((r = grow(d_plevel_, nc, n, 0))) return r;
+  if ((r = grow(d_origin_, nc, n, 0))) return r;
+  if ((r = grow(d_locks_, nc, n, 0))) return r;
+  cap_ = nc;
+  return 0;
+}
+
+int Index::ensure_upper(size_t need) {
+  if (need <= cap_ul_) return 0;
+  size_t nc = std::max(need, std::max<size_t>(cap_ul_ * 2, 1024));
+  int r;
+  if ((r = grow(d_adjU_, nc * M, n_ul * M, 0xFF))) return r;
+  if ((r = grow(d_adjUd_, nc * M, n_ul * M, 0))) return r;
+  cap_ul_ = nc;
+  return 0;
+}
+
+int Index::ensure_visited(size_t slots, size_t cap_entries) {
+  if (slots <= vis_slots_ && cap_entries <= vis_cap_) return 0;
+  size_t ns = std::max(slots, vis_slots_), nc = std::max(cap_entries, vis_cap_);
+  HB_CUDA(cudaStreamSynchronize(stream_));
+  cudaFree(d_vis_tab_);
+  cudaFree(d_vis_epoch_);
+  d_vis_tab_ = d_vis_epoch_ = nullptr;
+  vis_slots_ = vis_cap_ = 0;
+  HB_CUDA(cudaMalloc(&d_vis_tab_, ns * nc * sizeof(uint32_t)));
+  HB_CUDA(cudaMalloc(&d_vis_epoch_, ns * sizeof(uint32_t)));
+  HB_CUDA(cudaMemsetAsync(d_vis_tab_, 0, ns * nc * sizeof(uint32_t), stream_));
+  // epoch = max forces a table clear on first use whatever id_bits is (Visited::begin)
+  HB_CUDA(cudaMemsetAsync(d_vis_epoch_, 0xFF, ns * sizeof(uint32_t), stream_));
+  vis_slots_ = ns;
+  vis_cap_ = nc;
+  return 0;
+}
+
+int Index::fill_visited_cfg(VisitedCfg& c) {
+  const int id_bits = std::max(1, ilog2(std::max<size_t>(cap_, 2)));
+  if (id_bits != vis_id_bits_) {  // entries are (epoch << id_bits) | id: a new split invalidates every table
+    HB_CUDA(cudaMemsetAsync(d_vis_epoch_, 0xFF, vis_slots_ * sizeof(uint32_t), stream_));
+    vis_id_bits_ = id_bits;
+  }
+  c.tables = d_vis_tab_;
+  c.epochs = d_vis_epoch_;
+  c.cap = (uint32_t)vis_cap_;
+  c.shift = 32 - ilog2(vis_cap_);
+  c.id_bits = id_bits;
+  return 0;
+}
+
+int Index::ensure_scratch(void** p, size_t* cur, size_t need) {
+  if (need <= *cur) return 0;
+  HB_CUDA(cudaStreamSynchronize(stream_));
+  cudaFree(*p);
+  *p = nullptr;
+  *cur = 0;
+  size_t nb = std::max(need, (size_t)4096);
+  HB_CUDA(cudaMalloc(p, nb));
+  *cur = nb;
+  return 0;
+}
+
+GraphView Index::view() const {
+  GraphView g;
+  g.vec = d_vec_.p;
+  g.d4 = d_pad / 4;
+  g.adj0 = d_adj0_.p;
+  g.adj0_d = d_adj0d_.p;
+  g.deg0 = 2 * M;
+  g.adjU = d_adjU_.p;
+  g.adjU_d = d_adjUd_.p;
+  g.M = M;
+  g.up_off = d_upoff_.p;
+  g.plevel = d_plevel_.p;
+  g.level = d_level_.p;
+  g.origin = d_origin_.p;
+  g.n = (uint32_t)n;
+  g.entry = entry;
+  g.entry_level = entry_level;
+  return g;
+}
+
+// LayerGenerator::generate, hnsw.rs:363-374 (law only; the reference's StdRng stream needs the rand crate)
+int Index::draw_level() {
+  double xsi = rng.unif();
+  if (xsi <= 0.) xsi = 1e-300;
+  double level = -std::log(xsi) * level_scale;
+  size_t ul = (size_t)std::floor(level);
+  if (ul >= (size_t)max_layer) ul = (size_t)(rng.next() % (uint64_t)max_layer);
+  return (int)ul;
+}
+
+// ------------------------------------------------------------------------------------------------
+// insert
+int Index::grow_plevel(uint32_t id, int new_pl) {
+  const int old = h_plevel[id];
+  if (new_pl <= old) return 0;
+  int r;
+  if ((r = ensure_upper(n_ul + new_pl))) return r;
+  if (old > 0) {
+    const size_t src = (size_t)h_upoff[id] * M, dst = n_ul * M, cnt = (size_t)old * M;
+    HB_CUDA(cudaMemcpyAsync(d_adjU_.p + dst, d_adjU_.p + src, cnt * 4, cudaMemcpyDeviceToDevice, stream_));
+    HB_CUDA(cudaMemcpyAsync(d_adjUd_.p + dst, d_adjUd_.p + src, cnt * 4, cudaMemcpyDeviceToDevice, stream_));
+  }
+  h_upoff[id] = (uint32_t)n_ul;
+  h_plevel[id] = (uint8_t)new_pl;
+  n_ul += new_pl;
+  HB_CUDA(cudaMemcpyAsync(d_upoff_.p + id, &h_upoff[id], 4, cudaMemcpyHostToDevice, stream_));
+  HB_CUDA(cudaMemcpyAsync(d_plevel_.p + id, &h_plevel[id], 1, cudaMemcpyHostToDevice, stream_));
+  HB_CUDA(cudaStreamSynchronize(stream_));
+  return 0;
+}
+
+int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16_t>& masks, size_t mask_off) {
+  (void)masks;
+  InsertParams p;
+  p.g = view();
+  p.first = (uint32_t)first;
+  p.count = (uint32_t)count;
+  p.layer_mask = reinterpret_cast<const uint16_t*>(d_mask_) + mask_off;
+  p.ef_c = ef_c;
+  p.keep_pruned = keep_pruned ? 1 : 0;
+  p.work_counter = d_counter_;
+  p.locks = d_locks_.p;
+  p.stats = nullptr;
+  p.status = d_status_;
+  const size_t spw = insert_smem_per_warp(p.g.d4, ef_c, p.g.deg0);
+  p.smem_per_warp = (int)spw;
+  const size_t smem = spw * (BUILD_THREADS / 32);
+  if (smem > 220 * 1024) return fail("ef_construction / dimension too large for the insert kernel's shared memory");
+  int bps = 0;
+  HB_CUDA(launch_insert_search(p, metric, 0, smem, stream_, true, &bps));
+  if (bps < 1) return fail("insert kernel does not fit on an SM");
+  const int wpb = BUILD_THREADS / 32;
+  int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (count + wpb - 1) / wpb);
+  size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)2 * (ef_c + 16) * p.g.deg0));
+  for (int attempt = 0;; ++attempt) {
+    int r;
+    if ((r = ensure_visited((size_t)grid * wpb, vcap))) return r;
+    if ((r = fill_visited_cfg(p.vis))) return r;
+    HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
+    HB_CUDA(launch_insert_search(p, metric, grid, smem, stream_, false, nullptr));
+    int status = 0;
+    HB_CUDA(cudaMemcpyAsync(&status, d_status_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    HB_CUDA(cudaStreamSynchronize(stream_));
+    if (status == 0) break;
+    if (attempt >= 8) return fail("visited table overflow persists");
+    HB_CUDA(cudaMemsetAsync(d_status_, 0, sizeof(int), stream_));
+    vcap = vis_cap_ * 2;  // rare: a search wandered further than 2*(ef+16)*degree nodes
+  }
+  int lgrid = (int)std::min<size_t>((size_t)sm_count_ * 8, (count + wpb - 1) / wpb);
+  HB_CUDA(launch_insert_link(p, lgrid, stream_));
+  return 0;
+}
+
+int Index::insert_batch(const float* vecs, size_t n_new, size_t stride, const float* const* rows, const uint64_t* ids,
+                        const int32_t* levels) {
+  if (n_new == 0) return 0;
+  if (dim == 0) return fail("dimension not set");
+  HB_CUDA(cudaSetDevice(device));
+  // ---- levels, PointId ranks, upper-list allocation (generate_new_point, hnsw.rs:503-531)
+  std::vector<int> lv(n_new);
+  size_t need_ul = 0;
+  for (size_t i = 0; i < n_new; ++i) {
+    int l = levels ? levels[i] : draw_level();
+    if (l < 0) l = 0;
+    if (l >= max_layer) l = max_layer - 1;
+    lv[i] = l;
+    need_ul += l;
+  }
+  int r;
+  if ((r = ensure_points(n + n_new))) return r;
+  if ((r = ensure_upper(n_ul + need_ul + 2 * MAX_LAYERS))) return r;
+  const size_t first = n;
+  h_level.resize(first + n_new);
+  h_plevel.resize(first + n_new);
+  h_rank.resize(first + n_new);
+  h_origin.resize(first + n_new);
+  h_upoff.resize(first + n_new);
+  std::vector<uint16_t> masks(n_new);
+  for (size_t i = 0; i < n_new; ++i) {
+    const size_t id = first + i;
+    h_level[id] = (uint8_t)lv[i];
+    h_plevel[id] = (uint8_t)lv[i];
+    h_rank[id] = (int32_t)layer_count[lv[i]];
+    layer_count[lv[i]]++;
+    h_origin[id] = ids ? ids[i] : (uint64_t)id;
+    if (lv[i] > 0) {
+      h_upoff[id] = (uint32_t)n_ul;
+      n_ul += lv[i];
+    } else {
+      h_upoff[id] = INVALID_ID;
+    }
+    uint16_t m = 0;
+    for (int l = 0; l < MAX_LAYERS; ++l)
+      if (layer_count[l] > 0) m |= (uint16_t)(1u << l);
+    masks[i] = m;
+  }
+  // ---- upload vectors (rows padded to d_pad on the device; the padding was zero-filled at allocation)
+  if (rows) {
+    const size_t chunk = std::max<size_t>(1, (size_t)(8u << 20) / ((size_t)dim * 4));
+    if (h_pin_bytes_ < chunk * dim * 4) {
+      if (h_pin_) cudaFreeHost(h_pin_);
+      h_pin_ = nullptr;
+      h_pin_bytes_ = 0;
+      HB_CUDA(cudaMallocHost(&h_pin_, chunk * dim * 4));
+      h_pin_bytes_ = chunk * dim * 4;
+    }
+    for (size_t b = 0; b < n_new; b += chunk) {
+      const size_t c = std::min(chunk, n_new - b);
+      float* st = (float*)h_pin_;
+      for (size_t i = 0; i < c; ++i) memcpy(st + i * dim, rows[b + i], (size_t)dim * 4);
+      HB_CUDA(cudaMemcpy2DAsync(d_vec_.p + (first + b) * d_pad, (size_t)d_pad * 4, st, (size_t)dim * 4, (size_t)dim * 4, c,
+                                cudaMemcpyHostToDevice, stream_));
+      HB_CUDA(cudaStreamSynchronize(stream_));
+    }
+  } else {
+    HB_CUDA(cudaMemcpy2DAsync(d_vec_.p + first * d_pad, (size_t)d_pad * 4, vecs, stride * 4, (size_t)dim * 4, n_new,
+                              cudaMemcpyHostToDevice, stream_));
+  }
+  HB_CUDA(cudaMemcpyAsync(d_level_.p + first, h_level.data() + first, n_new, cudaMemcpyHostToDevice, stream_));
+  HB_CUDA(cudaMemcpyAsync(d_plevel_.p + first, h_plevel.data() + first, n_new, cudaMemcpyHostToDevice, stream_));
+  HB_CUDA(cudaMemcpyAsync(d_origin_.p + first, h_origin.data() + first, n_new * 8, cudaMemcpyHostToDevice, stream_));
+  HB_CUDA(cudaMemcpyAsync(d_upoff_.p + first, h_upoff.data() + first, n_new * 4, cudaMemcpyHostToDevice, stream_));
+  if ((r = ensure_scratch(&d_mask_, &d_mask_bytes_, n_new * 2))) return r;
+  HB_CUDA(cudaMemcpyAsync(d_mask_, masks.data(), n_new * 2, cudaMemcpyHostToDevice, stream_));
+  n = first + n_new;  // stored; points become reachable as their batch links them
+  // ---- schedule batches
+  size_t done = 0;
+  while (done < n_new) {
+    const size_t id = first + done;
+    if (entry == INVALID_ID) {  // very first point: becomes the entry point (hnsw.rs:1106-1109)
+      entry = (uint32_t)id;
+      entry_level = lv[done];
+      done++;
+      continue;
+    }
+    const size_t linked = first + done;
+    size_t nb = std::min<size_t>(std::max<size_t>(linked / std::max<uint32_t>(batch_ratio, 1), 1), batch_max);
+    nb = std::min(nb, n_new - done);
+    bool promo = false;
+    for (size_t j = 0; j < nb; ++j) {
+      if (lv[done + j] > entry_level) {  // a new top level: alone in its batch (check_entry_point, hnsw.rs:534-557)
+        if (j == 0) {
+          nb = 1;
+          promo = true;
+        } else {
+          nb = j;
+        }
+        break;
+      }
+    }
+    if (promo && (r = grow_plevel(entry, lv[done]))) return r;  // old entry point gains lists up to the new top
+    if ((r = run_insert_range(id, nb, masks, done))) return r;
+    if (promo) {
+      entry = (uint32_t)id;
+      entry_level = lv[done];
+    }
+    done += nb;
+  }
+  HB_CUDA(cudaStreamSynchronize(stream_));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// import of a graph built elsewhere (oracle, another rank, a dump)
+int Index::import_graph(const float* vecs, size_t n_new, int d, const uint64_t* origin, const uint8_t* levels,
+                        int64_t entry_id, int nlayers, const uint64_t* const* offsets, const uint32_t* const* ids,
+                        const float* const* dists) {
+  if (n != 0) return fail("import_graph needs an empty index");
+  if (n_new == 0) return 0;
+  HB_CUDA(cudaSetDevice(device));
+  int r;
+  if ((r = set_dim(d))) return r;
+  if (nlayers > MAX_LAYERS) nlayers = MAX_LAYERS;
+  // present level: plevel[p] = highest layer at which p can be visited = max(level, highest layer l where p
+  // appears in the layer-l list of a point present at l).  Fixpoint per layer, top down.
+  std::vector<uint8_t> pl(levels, levels + n_new);
+  for (int l = nlayers - 1; l >= 1; --l) {
+    std::vector<uint32_t> work;
+    std::vector<uint8_t> in(n_new, 0);
+    for (size_t p = 0; p < n_new; ++p)
+      if (pl[p] >= l) {
+        in[p] = 1;
+        work.push_back((uint32_t)p);
+      }
+    while (!work.empty()) {
+      uint32_t q = work.back();
+      work.pop_back();
+      for (uint64_t j = offsets[l][q]; j < offsets[l][q + 1]; ++j) {
+        uint32_t p = ids[l][j];
+        if (p < n_new && !in[p]) {
+          in[p] = 1;
+          if (pl[p] < l) pl[p] = (uint8_t)l;
+          work.push_back(p);
+        }
+      }
+    }
+  }
+  size_t need_ul = 0;
+  for (size_t p = 0; p < n_new; ++p) need_ul += pl[p];
+  if ((r = ensure_points(n_new))) return r;
+  if ((r = ensure_upper(need_ul + 2 * MAX_LAYERS))) return r;
+  const size_t deg0 = (size_t)2 * M;
+  h_level.assign(levels, levels + n_new);
+  h_plevel = pl;
+  h_rank.resize(n_new);
+  h_origin.assign(origin, origin + n_new);
+  h_upoff.resize(n_new);
+  for (int l = 0; l < MAX_LAYERS; ++l) layer_count[l] = 0;
+  n_ul = 0;
+  for (size_t p = 0; p < n_new; ++p) {
+    h_rank[p] = (int32_t)layer_count[levels[p]]++;
+    if (pl[p] > 0) {
+      h_upoff[p] = (uint32_t)n_ul;
+      n_ul += pl[p];
+    } else {
+      h_upoff[p] = INVALID_ID;
+    }
+  }
+  std::vector<uint32_t> a0(n_new * deg0, INVALID_ID), aU(std::max<size_t>(n_ul, 1) * M, INVALID_ID);
+  std::vector<float> a0d(n_new * deg0, 0.f), aUd(std::max<size_t>(n_ul, 1) * M, 0.f);
+  for (size_t p = 0; p < n_new; ++p) {
+    if (nlayers > 0) {
+      uint64_t b = offsets[0][p], e = offsets[0][p + 1];
+      if (e - b > deg0) return fail("layer-0 list longer than 2*max_nb_connection");
+      for (uint64_t j = b; j < e; ++j) {
+        a0[p * deg0 + (j - b)] = ids[0][j];
+        if (dists && dists[0]) a0d[p * deg0 + (j - b)] = dists[0][j];
+      }
+    }
+    for (int l = 1; l <= pl[p] && l < nlayers; ++l) {
+      uint64_t b = offsets[l][p], e = offsets[l][p + 1];
+      if (e - b > (uint64_t)M) return fail("upper-layer list longer than max_nb_connection");
+      const size_t li = (size_t)h_upoff[p] + (l - 1);
+      for (uint64_t j = b; j < e; ++j) {
+        aU[li * M + (j - b)] = ids[l][j];
+        if (dists && dists[l]) aUd[li * M + (j - b)] = dists[l][j];
+      }
+    }
+  }
+  HB_CUDA(cudaMemcpy2DAsync(d_vec_.p, (size_t)d_pad * 4, vecs, (size_t)dim * 4, (size_t)dim * 4, n_new, cudaMemcpyHostToDevice, stream_));
+  HB_CUDA(cudaMemcpyAsync(d_adj0_.p, a0.data(), a0.size() * 4, cudaMemcpyHostToDevice, stream_));
+  HB_CUDA(cudaMemcpyAsync(d_adj0d_.p, a0d.data(), a0d.size() * 4, cudaMemcpyHostToDevice, stream_));
+  if (n_ul) {
+    HB_CUDA(cudaMemcpyAsync(d_adjU_.p, aU.data(), n_ul * M * 4, cudaMemcpyHostToDevice, stream_));
+    HB_CUDA(cudaMemcpyAsync(d_adjUd_.p, aUd.data(), n_ul * M * 4, cudaMemcpyHostToDevice, stream_));
+  }
+  HB_CUDA(cudaMemcpyAsync(d_level_.p, h_level.data(), n_new, cudaMemcpyHostToDevice, stream_));
+  HB_CUDA(cudaMemcpyAsync(d_plevel_.p, h_plevel.data(), n_new, cudaMemcpyHostToDevice, stream_));
+  HB_CUDA(cudaMemcpyAsync(d_origin_.p, h_origin.data(), n_new * 8, cudaMemcpyHostToDevice, stream_));
+  HB_CUDA(cudaMemcpyAsync(d_upoff_.p, h_upoff.data(), n_new * 4, cudaMemcpyHostToDevice, stream_));
+  HB_CUDA(cudaStreamSynchronize(stream_));
+  n = n_new;
+  if (entry_id >= 0 && (size_t)entry_id < n_new) {
+    entry = (uint32_t)entry_id;
+    entry_level = levels[entry_id];
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// search
+int Index::search_device(const float* d_queries, size_t nq, size_t k, size_t ef_arg, const uint32_t* d_filter_bits,
+                         NeighbourOut* d_out, int32_t* d_counts, bool sync, float* kernel_ms) {
+  if (nq == 0) return 0;
+  if (k == 0) return fail("knbn must be positive");
+  if (d_filter_bits) return fail("filtered search kernel not available in this build");
+  HB_CUDA(cudaSetDevice(device));
+  if (dim == 0) {  // empty index: every answer is empty (hnsw.rs:1498-1503)
+    HB_CUDA(cudaMemsetAsync(d_counts, 0, nq * sizeof(int32_t), stream_));
+    if (sync) HB_CUDA(cudaStreamSynchronize(stream_));
+    return 0;
+  }
+  SearchParams p;
+  p.g = view();
+  p.queries = d_queries;
+  p.d = dim;
+  p.q_stride = dim;
+  p.nq = (uint32_t)nq;
+  p.k = (int)k;
+  p.ef = (int)std::max(ef_arg, k);  // hnsw.rs:1531
+  int layer0 = 0;                   // hnsw.rs:1534-1540
+  while (layer0 < MAX_LAYERS - 1 && layer_count[layer0] == 0) layer0++;
+  if (n == 0) layer0 = 0;
+  p.layer0 = layer0;
+  p.work_counter = d_counter_;
+  p.out_nb = d_out;
+  p.out_count = d_counts;
+  p.filter_bits = d_filter_bits;
+  p.stats = stats_on_ ? d_stats_ : nullptr;
+  p.status = d_status_;
+  size_t spw = (search_smem_per_warp(p.g.d4, p.ef) + 15) & ~(size_t)15;
+  p.smem_per_warp = (int)spw;
+  const int wpb = SEARCH_THREADS / 32;
+  const size_t smem = spw * wpb;
+  if (smem > 220 * 1024) return fail("ef / dimension too large for the search kernel's shared memory");
+  int bps = 0;
+  HB_CUDA(launch_search(p, metric, 0, smem, stream_, true, &bps));
+  if (bps < 1) return fail("search kernel does not fit on an SM");
+  const int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (nq + wpb - 1) / wpb);
+  const int deg = layer0 == 0 ? 2 * M : M;
+  size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)2 * (p.ef + 16) * deg));
+  for (int attempt = 0;; ++attempt) {
+    int r;
+    if ((r = ensure_visited((size_t)grid * wpb, vcap))) return r;
+    if ((r = fill_visited_cfg(p.vis))) return r;
+    HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
+    HB_CUDA(cudaEventRecord(ev0_, stream_));
+    HB_CUDA(launch_search(p, metric, grid, smem, stream_, false, nullptr));
+    HB_CUDA(cudaEventRecord(ev1_, stream_));
+    if (!sync) break;
+    int status = 0;
+    HB_CUDA(cudaMemcpyAsync(&status, d_status_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    HB_CUDA(cudaStreamSynchronize(stream_));
+    if (status == 0) {
+      if (kernel_ms) HB_CUDA(cudaEventElapsedTime(kernel_ms, ev0_, ev1_));
+      break;
+    }
+    if (attempt >= 8) return fail("visited table overflow persists");
+    HB_CUDA(cudaMemsetAsync(d_status_, 0, sizeof(int), stream_));
+    vcap = vis_cap_ * 2;
+  }
+  stat_queries_ += stats_on_ ? nq : 0;
+  return 0;
+}
+
+int Index::search_host(const float* queries, const float* const* rows, size_t nq, int d, size_t k, size_t ef,
+                       const uint32_t* filter_bits_host, NeighbourOut* out, int32_t* counts) {
+  if (nq == 0) return 0;
+  HB_CUDA(cudaSetDevice(device));
+  if (dim != 0 && d != dim) return fail("query length differs from the index dimension");
+  if (dim == 0) {
+    for (size_t i = 0; i < nq; ++i) counts[i] = 0;
+    return 0;
+  }
+  int r;
+  const size_t qbytes = nq * (size_t)dim * 4;
+  if ((r = ensure_scratch(&d_q_, &d_q_bytes_, qbytes))) return r;
+  if ((r = ensure_scratch(&d_out_, &d_out_bytes_, nq * k * sizeof(NeighbourOut)))) return r;
+  if ((r = ensure_scratch(&d_cnt_, &d_cnt_bytes_, nq * sizeof(int32_t)))) return r;
+  if (rows) {
+    if (h_pin_bytes_ < qbytes) {
+      if (h_pin_) cudaFreeHost(h_pin_);
+      h_pin_ = nullptr;
+      h_pin_bytes_ = 0;
+      HB_CUDA(cudaMallocHost(&h_pin_, qbytes));
+      h_pin_bytes_ = qbytes;
+    }
+    float* st = (float*)h_pin_;
+    for (size_t i = 0; i < nq; ++i) memcpy(st + i * dim, rows[i], (size_t)dim * 4);
+    HB_CUDA(cudaMemcpyAsync(d_q_, st, qbytes, cudaMemcpyHostToDevice, stream_));
+  } else {
+    HB_CUDA(cudaMemcpyAsync(d_q_, queries, qbytes, cudaMemcpyHostToDevice, stream_));
+  }
+  const uint32_t* dfb = nullptr;
+  if (filter_bits_host) {
+    const size_t fb = ((n + 31) / 32) * 4;
+    if ((r = ensure_scratch(&d_fbits_, &d_fbits_bytes_, fb))) return r;
+    HB_CUDA(cudaMemcpyAsync(d_fbits_, filter_bits_host, fb, cudaMemcpyHostToDevice, stream_));
+    dfb = (const uint32_t*)d_fbits_;
+  }
+  if ((r = search_device((const float*)d_q_, nq, k, ef, dfb, (NeighbourOut*)d_out_, (int32_t*)d_cnt_, true, nullptr))) return r;
+  HB_CUDA(cudaMemcpyAsync(out, d_out_, nq * k * sizeof(NeighbourOut), cudaMemcpyDeviceToHost, stream_));
+  HB_CUDA(cudaMemcpyAsync(counts, d_cnt_, nq * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+  HB_CUDA(cudaStreamSynchronize(stream_));
+  return 0;
+}
+
+int Index::make_filter_bits(int mode, const uint64_t* sorted_ids, size_t nids, int (*fn)(uint64_t, void*), void* ctx,
+                            std::vector<uint32_t>& bits) const {
+  bits.assign((n + 31) / 32 + 1, 0u);
+  for (size_t i = 0; i < n; ++i) {
+    bool pass;
+    if (mode == 2) {
+      if (!fn) return fail("filter callback is NULL");
+      pass = fn(h_origin[i], ctx) != 0;  // Fn(&DataId)->bool, filter.rs:17-24
+    } else {
+      pass = std::binary_search(sorted_ids, sorted_ids + nids, h_origin[i]);  // Vec<usize> filter, filter.rs:11-15
+    }
+    if (pass) bits[i >> 5] |= 1u << (i & 31);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// export
+int Index::export_layer(int layer, uint64_t* offsets, uint32_t* ids, float* dists, int64_t* total) const {
+  if (layer < 0 || layer >= MAX_LAYERS) return fail("bad layer");
+  cudaSetDevice(device);
+  const size_t deg0 = (size_t)2 * M;
+  std::vector<uint32_t> a;
+  std::vector<float> ad;
+  if (layer == 0) {
+    a.resize(n * deg0);
+    ad.resize(n * deg0);
+    if (n) {
+      HB_CUDA(cudaMemcpy(a.data(), d_adj0_.p, a.size() * 4, cudaMemcpyDeviceToHost));
+      HB_CUDA(cudaMemcpy(ad.data(), d_adj0d_.p, ad.size() * 4, cudaMemcpyDeviceToHost));
+    }
+  } else {
+    a.resize(n_ul * M);
+    ad.resize(n_ul * M);
+    if (n_ul) {
+      HB_CUDA(cudaMemcpy(a.data(), d_adjU_.p, a.size() * 4, cudaMemcpyDeviceToHost));
+      HB_CUDA(cudaMemcpy(ad.data(), d_adjUd_.p, ad.size() * 4, cudaMemcpyDeviceToHost));
+    }
+  }
+  uint64_t o = 0;
+  for (size_t p = 0; p < n; ++p) {
+    if (offsets) offsets[p] = o;
+    const uint32_t* l = nullptr;
+    const float* ld = nullptr;
+    size_t cap = 0;
+    if (layer == 0) {
+      l = a.data() + p * deg0;
+      ld = ad.data() + p * deg0;
+      cap = deg0;
+    } else if (layer <= h_plevel[p]) {
+      const size_t li = (size_t)h_upoff[p] + (layer - 1);
+      l = a.data() + li * M;
+      ld = ad.data() + li * M;
+      cap = M;
+    }
+    for (size_t j = 0; j < cap && l[j] != INVALID_ID; ++j) {
+      if (ids) ids[o] = l[j];
+      if (dists) dists[o] = ld[j];
+      ++o;
+    }
+  }
+  if (offsets) offsets[n] = o;
+  if (total) *total = (int64_t)o;
+  return 0;
+}
+
+int Index::export_vectors(float* out) const {
+  if (n == 0) return 0;
+  cudaSetDevice(device);
+  HB_CUDA(cudaMemcpy2D(out, (size_t)dim * 4, d_vec_.p, (size_t)d_pad * 4, (size_t)dim * 4, n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int Index::enable_stats(bool on) {
+  stats_on_ = on;
+  return 0;
+}
+
+int Index::get_stats(uint64_t* out4, bool reset) {
+  cudaSetDevice(device);
+  unsigned long long h[4];
+  HB_CUDA(cudaStreamSynchronize(stream_));
+  HB_CUDA(cudaMemcpy(h, d_stats_, sizeof(h), cudaMemcpyDeviceToHost));
+  out4[0] = h[0];
+  out4[1] = h[1];
+  out4[2] = h[2];
+  out4[3] = stat_queries_;
+  if (reset) {
+    HB_CUDA(cudaMemset(d_stats_, 0, sizeof(h)));
+    stat_queries_ = 0;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// replication blobs: 0 vec, 1 adj0, 2 adjU, 3 up_off, 4 plevel, 5 level, 6 origin, 7 adj0_d, 8 adjU_d
+static const uint64_t BLOB_MAGIC = 0x68623230306e7377ull;
+
+int Index::blob_header(uint64_t* h) const {
+  for (int i = 0; i < 16; ++i) h[i] = 0;
+  h[0] = BLOB_MAGIC;
+  h[1] = n;
+  h[2] = (uint64_t)dim;
+  h[3] = (uint64_t)M;
+  h[4] = (uint64_t)max_layer;
+  h[5] = (uint64_t)ef_c;
+  h[6] = (uint64_t)metric;
+  h[7] = n_ul;
+  h[8] = entry;
+  h[9] = (uint64_t)(int64_t)entry_level;
+  h[10] = 1;  // distances included
+  return 0;
+}
+
+int Index::blob_alloc(const uint64_t* h) {
+  if (h[0] != BLOB_MAGIC) return fail("bad replication header");
+  if (n != 0) return fail("blob_alloc needs an empty index");
+  if ((int)h[3] != M || (int)h[6] != metric) return fail("replication header does not match this handle's M / metric");
+  HB_CUDA(cudaSetDevice(device));
+  int r;
+  if ((r = set_dim((int)h[2]))) return r;
+  if ((r = ensure_points((size_t)h[1]))) return r;
+  if ((r = ensure_upper((size_t)h[7] + 2 * MAX_LAYERS))) return r;
+  n = (size_t)h[1];
+  n_ul = (size_t)h[7];
+  entry = (uint32_t)h[8];
+  entry_level = (int)(int64_t)h[9];
+  max_layer = (int)h[4];
+  ef_c = (int)h[5];
+  return 0;
+}
+
+int Index::blob_info(int i, void** p, uint64_t* bytes) const {
+  const size_t deg0 = (size_t)2 * M;
+  switch (i) {
+    case 0: *p = d_vec_.p; *bytes = n * d_pad * 4; return 0;
+    case 1: *p = d_adj0_.p; *bytes = n * deg0 * 4; return 0;
+    case 2: *p = d_adjU_.p; *bytes = n_ul * M * 4; return 0;
+    case 3: *p = d_upoff_.p; *bytes = n * 4; return 0;
+    case 4: *p = d_plevel_.p; *bytes = n; return 0;
+    case 5: *p = d_level_.p; *bytes = n; return 0;
+    case 6: *p = d_origin_.p; *bytes = n * 8; return 0;
+    case 7: *p = d_adj0d_.p; *bytes = n * deg0 * 4; return 0;
+    case 8: *p = d_adjUd_.p; *bytes = n_ul * M * 4; return 0;
+  }
+  return fail("bad blob index");
+}
+
+int Index::blob_commit() {
+  cudaSetDevice(device);
+  h_level.resize(n);
+  h_plevel.resize(n);
+  h_origin.resize(n);
+  h_upoff.resize(n);
+  h_rank.resize(n);
+  if (n) {
+    HB_CUDA(cudaMemcpy(h_level.data(), d_level_.p, n, cudaMemcpyDeviceToHost));
+    HB_CUDA(cudaMemcpy(h_plevel.data(), d_plevel_.p, n, cudaMemcpyDeviceToHost));
+    HB_CUDA(cudaMemcpy(h_origin.data(), d_origin_.p, n * 8, cudaMemcpyDeviceToHost));
+    HB_CUDA(cudaMemcpy(h_upoff.data(), d_upoff_.p, n * 4, cudaMemcpyDeviceToHost));
+  }
+  for (int l = 0; l < MAX_LAYERS; ++l) layer_count[l] = 0;
+  for (size_t p = 0; p < n; ++p) h_rank[p] = (int32_t)layer_count[h_level[p]]++;
+  return 0;
+}
+
+}  // namespace hb

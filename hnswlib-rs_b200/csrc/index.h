@@ -1,0 +1,153 @@
+// Host side of the engine: owns the HBM-resident index, schedules insert batches and query
+// launches.  Replaces, above the kernels, what PointIndexation / Hnsw::new / parallel_insert /
+// parallel_search do on the CPU in the reference (/root/reference/src/hnsw.rs:395-557, 739-905,
+// 1224-1238, 1612-1635): point bookkeeping (level draw, PointId ranks, entry point), and the
+// rayon fan-out, which here is a persistent-warp kernel launch.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace hb {
+
+struct SplitMix64 {
+  uint64_t s;
+  uint64_t next() {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  }
+  double unif() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+template <class T>
+struct DevArray {  // growable device array, contents preserved on growth
+  T* p = nullptr;
+  size_t cap = 0;
+};
+
+class Index {
+ public:
+  Index(int M, size_t max_elements, int max_layer, int ef_c, int metric, int device);
+  ~Index();
+  bool ok() const { return ok_; }
+
+  // ---- configuration (Hnsw::new and setters, hnsw.rs:771-905)
+  int M, max_layer, ef_c, metric, device;
+  size_t max_elements;
+  bool extend_candidates = false, keep_pruned = false, searching = false;
+  double level_scale;  // 1/ln(M) * factor
+  SplitMix64 rng{397};
+  uint32_t batch_ratio = 16, batch_max = 16384;
+
+  // ---- state
+  int dim = 0, d_pad = 0;
+  size_t n = 0;          // points stored (all linked: inserts are synchronous per call)
+  size_t n_ul = 0;       // upper lists allocated
+  size_t layer_count[MAX_LAYERS];
+  uint32_t entry = INVALID_ID;
+  int entry_level = -1;
+  std::vector<uint8_t> h_level, h_plevel;
+  std::vector<int32_t> h_rank;
+  std::vector<uint64_t> h_origin;
+  std::vector<uint32_t> h_upoff;
+
+  // ---- operations (return 0 or a negative status; message in err())
+  int set_dim(int d);
+  int draw_level();
+  int insert_batch(const float* vecs, size_t n_new, size_t stride, const float* const* rows, const uint64_t* ids,
+                   const int32_t* levels);
+  int import_graph(const float* vecs, size_t n_new, int d, const uint64_t* origin, const uint8_t* levels,
+                   int64_t entry_id, int nlayers, const uint64_t* const* offsets, const uint32_t* const* ids,
+                   const float* const* dists);
+  // host queries (flat or row pointers); results to host NeighbourOut[nq][k] + counts
+  int search_host(const float* queries, const float* const* rows, size_t nq, int d, size_t k, size_t ef,
+                  const uint32_t* filter_bits_host, NeighbourOut* out, int32_t* counts);
+  int search_device(const float* d_queries, size_t nq, size_t k, size_t ef, const uint32_t* d_filter_bits,
+                    NeighbourOut* d_out, int32_t* d_counts, bool sync, float* kernel_ms);
+  // filter materialisation: bit per internal id from a sorted origin-id list or a callback
+  int make_filter_bits(int mode, const uint64_t* sorted_ids, size_t nids, int (*fn)(uint64_t, void*), void* ctx,
+                       std::vector<uint32_t>& bits) const;
+
+  int export_layer(int layer, uint64_t* offsets, uint32_t* ids, float* dists, int64_t* total) const;
+  int export_vectors(float* out) const;
+  int enable_stats(bool on);
+  int get_stats(uint64_t* out4, bool reset);
+
+  // replication blobs
+  int blob_header(uint64_t* h16) const;
+  int blob_alloc(const uint64_t* h16);
+  int blob_count() const { return 9; }
+  int blob_info(int i, void** p, uint64_t* bytes) const;
+  int blob_commit();
+
+  int dist_batch(const float* queries, size_t nq, int d, const uint32_t* cand, size_t m, float* out);
+  int bruteforce(const float* queries, size_t nq, int d, size_t k, uint32_t* out_ids, float* out_dist);
+
+  const std::string& err() const { return err_; }
+  GraphView view() const;
+  cudaStream_t stream() const { return stream_; }
+  mutable std::mutex mu;  // the C ABI allows calls from many host threads (hnsw.rs:830-833)
+
+ private:
+  int fail(const std::string& m) const;
+  int cuda_fail(cudaError_t e, const char* what) const;
+  int ensure_points(size_t need);
+  int ensure_upper(size_t need_lists);
+  int ensure_visited(size_t slots, size_t cap_entries);
+  int ensure_scratch(void** p, size_t* cur, size_t need);
+  int grow_plevel(uint32_t id, int new_plevel);
+  int run_insert_range(size_t first, size_t count, const std::vector<uint16_t>& masks, size_t mask_off);
+  template <class T>
+  int grow(DevArray<T>& a, size_t need_elems, size_t keep_elems, int fill_byte);
+
+  bool ok_ = false;
+  mutable std::string err_;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  int sm_count_ = 0;
+
+  size_t cap_ = 0, cap_ul_ = 0;
+  DevArray<float> d_vec_;
+  DevArray<uint32_t> d_adj0_, d_adjU_, d_upoff_;
+  DevArray<float> d_adj0d_, d_adjUd_;
+  DevArray<uint8_t> d_level_, d_plevel_;
+  DevArray<uint64_t> d_origin_;
+  DevArray<int> d_locks_;
+
+  // visited tables
+  uint32_t* d_vis_tab_ = nullptr;
+  uint32_t* d_vis_epoch_ = nullptr;
+  size_t vis_slots_ = 0, vis_cap_ = 0;
+  int vis_id_bits_ = 0;
+  int fill_visited_cfg(VisitedCfg& c);
+
+  // small device scratch
+  unsigned int* d_counter_ = nullptr;
+  int* d_status_ = nullptr;
+  unsigned long long* d_stats_ = nullptr;
+  bool stats_on_ = false;
+  uint64_t stat_queries_ = 0;
+
+  // staging
+  void* h_pin_ = nullptr;
+  size_t h_pin_bytes_ = 0;
+  void* d_q_ = nullptr;
+  size_t d_q_bytes_ = 0;
+  void* d_out_ = nullptr;
+  size_t d_out_bytes_ = 0;
+  void* d_cnt_ = nullptr;
+  size_t d_cnt_bytes_ = 0;
+  void* d_fbits_ = nullptr;
+  size_t d_fbits_bytes_ = 0;
+  void* d_mask_ = nullptr;
+  size_t d_mask_bytes_ = 0;
+};
+
+}  // namespace hb

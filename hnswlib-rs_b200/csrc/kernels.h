@@ -1,0 +1,69 @@
+// Host-visible declarations of the kernel launchers (search.cu, build.cu, aux.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace hb {
+
+constexpr int SEARCH_THREADS = 256;  // 8 warps = 8 queries in flight per CTA
+constexpr int BUILD_THREADS = 128;   // 4 warps = 4 inserts in flight per CTA
+
+// One answer slot.  Same 16-byte layout as the reference's #[repr(C)] Neighbour_api {id: usize, d: f32}
+// (/root/reference/src/libext.rs:64-71); the internal id rides in what is tail padding there.
+struct NeighbourOut {
+  uint64_t origin;
+  float dist;
+  uint32_t internal;
+};
+
+struct SearchParams {
+  GraphView g;
+  const float* queries;  // device, [nq][q_stride]
+  int d;
+  int q_stride;
+  uint32_t nq;
+  int k;
+  int ef;      // already max(ef_arg, k), hnsw.rs:1531
+  int layer0;  // lowest layer holding a point of exactly that level (hnsw.rs:1534-1540), normally 0
+  VisitedCfg vis;
+  unsigned int* work_counter;
+  NeighbourOut* out_nb;  // [nq][k]
+  int32_t* out_count;    // [nq]
+  const uint32_t* filter_bits;  // nullptr = no filter; bit per internal id
+  unsigned long long* stats;    // nullptr or [3]: evals, expansions, adjacency ids read
+  int* status;                  // set to 1 on visited-table overflow
+  int smem_per_warp;
+};
+
+inline size_t search_smem_per_warp(int d4, int ef) { return (size_t)d4 * 16 + (size_t)ef * 8 + 32 * 8; }
+
+struct InsertParams {
+  GraphView g;
+  uint32_t first;   // internal id of the first point of the batch
+  uint32_t count;   // points in the batch
+  const uint16_t* layer_mask;  // [count] bit l set <=> some point of exact level l exists when this point searches
+  int ef_c;
+  int keep_pruned;
+  VisitedCfg vis;
+  unsigned int* work_counter;
+  int* locks;  // [capacity] per-point spin locks (phase B)
+  unsigned long long* stats;
+  int* status;
+  int smem_per_warp;
+};
+
+inline size_t insert_smem_per_warp(int d4, int ef_c, int deg0) {
+  size_t b = (size_t)d4 * 32 + (size_t)ef_c * 8 + 256 + (size_t)deg0 * 12 + (size_t)ef_c * 2;
+  return (b + 15) & ~(size_t)15;
+}
+
+cudaError_t launch_insert_search(const InsertParams& p, int metric, int grid, size_t smem, cudaStream_t st,
+                                 bool query_only, int* blocks_per_sm);
+cudaError_t launch_insert_link(const InsertParams& p, int grid, cudaStream_t st);
+
+cudaError_t launch_search(const SearchParams& p, int metric, int grid, size_t smem, cudaStream_t st, bool query_only,
+                          int* blocks_per_sm);
+
+}  // namespace hb

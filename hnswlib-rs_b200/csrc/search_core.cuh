@@ -1,0 +1,87 @@
+// search_layer on a warp: the ef-bounded best-first expansion of one layer.
+// Restates /root/reference/src/hnsw.rs:922-1064 (search_layer) for one warp that owns the whole
+// queue state of one query; used by the query kernel (search.cu) and the insert kernel (build.cu).
+#pragma once
+#include "common.cuh"
+
+namespace hb {
+
+struct WarpSmem {
+  float4* q4;         // query, d4 float4 (zero padded)
+  uint64_t* wbuf;     // queue keys, capacity >= ef
+  uint32_t* cand_id;  // 32
+  float* cand_d;      // 32
+};
+
+struct Stats {
+  unsigned evals, expansions, adj;
+};
+
+// Unfiltered search_layer.  On return Q (in s.wbuf) holds min(ef, reached) keys ascending by
+// (dist, id).  Equivalence with the two-heap reference loop (no filter):
+//   * accept rule `d < d(f) || |W| < ef` + bounded W  == keep the ef smallest keys seen (SortedQueue)
+//   * C.pop() nearest-first + stop when d(c) > d(f)   == expand the nearest unexpanded entry of W until none is left:
+//     a candidate evicted from W has key > every key of the (full) W, and f only decreases afterwards,
+//     so it would trip the stop rule the moment it is popped.
+// Ties on distance are ordered by id (oracle MODE_DET).
+template <class Op, int CH, int U>
+__device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem& s, Visited& vis, SortedQueue& Q,
+                                             uint32_t ep, int ef, int layer, Stats& st, bool& overflow) {
+  const int lane = lane_id();
+  const float4* vec4 = reinterpret_cast<const float4*>(g.vec);
+  vis.begin();
+  if (lane == 0) s.cand_id[0] = ep;
+  __syncwarp();
+  warp_dists<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, 1, s.cand_d);  // hnsw.rs:952
+  __syncwarp();
+  st.evals += 1;
+  const float d0 = s.cand_d[0];
+  if (lane == 0) vis.test_and_set(ep);  // hnsw.rs:955-956
+  Q.reset(s.wbuf, ef);
+  if (lane == 0) s.wbuf[0] = make_key(d0, ep);  // hnsw.rs:958-967 (ep enters W and C)
+  Q.n = 1;
+  __syncwarp();
+  for (;;) {
+    const int idx = Q.first_unexpanded();  // C.pop(): nearest candidate (hnsw.rs:971)
+    if (idx < 0) break;                    // C empty (969) or stop rule (981-993), see header
+    const uint64_t ck = Q.w[idx];
+    const uint32_t c = key_id(ck);
+    __syncwarp();
+    if (lane == 0) Q.w[idx] = ck | 1ull;
+    __syncwarp();
+    int cap;
+    const uint32_t* ids = list_ids(g, c, layer, cap);  // hnsw.rs:1006
+    st.expansions += 1;
+    for (int base = 0; base < cap; base += 32) {  // hnsw.rs:1013, 32 neighbours at a time
+      const uint32_t nid = (base + lane < cap) ? ids[base + lane] : INVALID_ID;
+      const unsigned valid = __ballot_sync(FULL, nid != INVALID_ID);
+      st.adj += __popc(valid);
+      const bool fresh = (nid != INVALID_ID) && vis.test_and_set(nid);  // hnsw.rs:1016-1017
+      const unsigned m = __ballot_sync(FULL, fresh);
+      const int cnt = __popc(m);
+      if (cnt) {
+        const int pos = __popc(m & ((1u << lane) - 1u));
+        if (fresh) s.cand_id[pos] = nid;
+        __syncwarp();
+        warp_dists<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, cnt, s.cand_d);  // hnsw.rs:1026
+        __syncwarp();
+        st.evals += cnt;
+        const uint64_t key = lane < cnt ? make_key(s.cand_d[lane], s.cand_id[lane]) : ~0ull;
+        unsigned acc = __ballot_sync(FULL, lane < cnt && Q.accepts(key));  // hnsw.rs:1028
+        while (acc) {
+          const int j = __ffs(acc) - 1;
+          acc &= acc - 1;
+          const uint64_t kj = __shfl_sync(FULL, key, j);
+          if (Q.accepts(kj)) Q.insert(kj);  // hnsw.rs:1035-1053
+        }
+      }
+      if (valid != FULL) break;  // lists are dense prefixes terminated by INVALID_ID
+    }
+    if (vis.overflowing()) {
+      overflow = true;
+      break;
+    }
+  }
+}
+
+}  // namespace hb

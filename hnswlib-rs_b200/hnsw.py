@@ -1,0 +1,361 @@
+"""Host-side mirror of the reference's public interface over the C ABI of libhnsw_b200.so.
+
+Mirrors, name for name, `Hnsw<T,D>` and the `AnnT` trait of jean-pierreBoth/hnswlib-rs
+(/root/reference/src/hnsw.rs:739-905,1069-1071,1224-1238,1487-1635; /root/reference/src/api.rs:13-38)
+and `FilterT` (/root/reference/src/filter.rs:7-24) for f32 data.  Every call goes through the
+extern "C" symbols declared in include/hnsw_b200.h (ctypes); there is no CPU fallback — constructing
+an index without a usable CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libhnsw_b200.so")
+_LIB = None
+
+FILTER_FN = C.CFUNCTYPE(C.c_int, C.c_uint64, C.c_void_p)
+
+
+class Neighbour_api(C.Structure):  # libext.rs:64-71
+    _fields_ = [("id", C.c_size_t), ("d", C.c_float)]
+
+
+class Neighbourhood_api(C.Structure):  # libext.rs:82-87
+    _fields_ = [("nbgh", C.c_int64), ("neighbours", C.POINTER(Neighbour_api))]
+
+
+class Vec_api(C.Structure):  # libext.rs:58-62
+    _fields_ = [("len", C.c_int64), ("ptr", C.POINTER(Neighbourhood_api))]
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen libhnsw_b200.so (fails loudly when it has not been built)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(f"{_LIB_PATH} is missing: run __graft_entry__.build() (make -C hnswlib-rs_b200/csrc)")
+    L = C.CDLL(_LIB_PATH)
+    vp, u64, sz, i32, i64 = C.c_void_p, C.c_uint64, C.c_size_t, C.c_int, C.c_int64
+    L.init_hnsw_f32.restype = vp
+    L.init_hnsw_f32.argtypes = [sz, sz, sz, C.c_char_p]
+    L.new_hnsw_f32.restype = vp
+    L.new_hnsw_f32.argtypes = [sz, sz, sz, C.c_char_p, sz, sz]
+    L.drop_hnsw_f32.argtypes = [vp]
+    L.init_hnsw_ptrdist_f32.restype = vp
+    L.init_hnsw_ptrdist_f32.argtypes = [sz, sz, vp]
+    L.insert_f32.argtypes = [vp, sz, vp, sz]
+    L.parallel_insert_f32.argtypes = [vp, sz, sz, vp, vp]
+    L.search_neighbours_f32.restype = C.POINTER(Neighbourhood_api)
+    L.search_neighbours_f32.argtypes = [vp, sz, vp, sz, sz]
+    L.parallel_search_neighbours_f32.restype = C.POINTER(Vec_api)
+    L.parallel_search_neighbours_f32.argtypes = [vp, sz, i64, vp, sz, sz]
+    L.file_dump_f32.restype = i64
+    L.file_dump_f32.argtypes = [vp, sz, C.c_char_p]
+    L.hnsw_b200_last_error.restype = C.c_char_p
+    L.hnsw_b200_device_count.restype = i32
+    L.hnsw_b200_set_device.argtypes = [i32]
+    L.hnsw_b200_free_neighbourhood.argtypes = [vp]
+    L.hnsw_b200_free_vec_api.argtypes = [vp]
+    for name in ("set_extend_candidates", "set_keeping_pruned", "set_searching_mode", "enable_stats"):
+        getattr(L, "hnsw_b200_" + name).argtypes = [vp, i32]
+    L.hnsw_b200_modify_level_scale.argtypes = [vp, C.c_double]
+    L.hnsw_b200_set_level_seed.argtypes = [vp, u64]
+    L.hnsw_b200_get_nb_point.restype = u64
+    L.hnsw_b200_get_nb_point.argtypes = [vp]
+    L.hnsw_b200_get_max_level_observed.argtypes = [vp]
+    L.hnsw_b200_get_dim.argtypes = [vp]
+    L.hnsw_b200_set_insert_batching.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.hnsw_b200_insert_flat.argtypes = [vp, vp, u64, u64, vp, vp]
+    L.hnsw_b200_search_flat.argtypes = [vp, vp, u64, u64, u64, u64, i32, vp, u64, FILTER_FN, vp, vp, vp, vp, vp, vp]
+    L.hnsw_b200_search_device.argtypes = [vp, vp, u64, u64, u64, vp, vp, i32, vp]
+    L.hnsw_b200_get_stats.argtypes = [vp, vp, i32]
+    L.hnsw_b200_export_points.argtypes = [vp, vp, vp, vp, vp]
+    L.hnsw_b200_export_vectors.argtypes = [vp, vp]
+    L.hnsw_b200_layer_edges.restype = i64
+    L.hnsw_b200_layer_edges.argtypes = [vp, i32]
+    L.hnsw_b200_export_layer.argtypes = [vp, i32, vp, vp, vp]
+    L.hnsw_b200_import_graph.argtypes = [vp, vp, u64, u64, vp, vp, i64, i32, vp, vp, vp]
+    L.hnsw_b200_blob_header.argtypes = [vp, vp]
+    L.hnsw_b200_blob_alloc.argtypes = [vp, vp]
+    L.hnsw_b200_blob_count.argtypes = [vp]
+    L.hnsw_b200_blob_info.argtypes = [vp, i32, vp, vp]
+    L.hnsw_b200_blob_commit.argtypes = [vp]
+    L.hnsw_b200_dist_batch.argtypes = [vp, vp, u64, u64, vp, u64, vp]
+    L.hnsw_b200_bruteforce.argtypes = [vp, vp, u64, u64, u64, vp, vp]
+    _LIB = L
+    return L
+
+
+def last_error():
+    return load_library().hnsw_b200_last_error().decode("utf-8", "replace")
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class HnswError(RuntimeError):
+    pass
+
+
+class Neighbour:
+    """hnsw.rs:98-107: d_id (DataId), distance, p_id = PointId(level, rank)."""
+    __slots__ = ("d_id", "distance", "p_id")
+
+    def __init__(self, d_id, distance, p_id):
+        self.d_id, self.distance, self.p_id = d_id, distance, p_id
+
+    def get_origin_id(self):
+        return self.d_id
+
+    def get_distance(self):
+        return self.distance
+
+    def __repr__(self):
+        return f"Neighbour(d_id={self.d_id}, distance={self.distance!r}, p_id={self.p_id})"
+
+
+class Hnsw:
+    """Hnsw<f32, D>: D given by name ("DistL2", "DistDot", "DistCosine", "DistL1", ...)."""
+
+    def __init__(self, max_nb_connection, max_elements, max_layer, ef_construction, dist_name, device=None):
+        L = load_library()
+        if device is not None:
+            if L.hnsw_b200_set_device(int(device)) != 0:
+                raise HnswError(last_error())
+        name = dist_name.encode()
+        self._L = L
+        self._h = L.new_hnsw_f32(int(max_nb_connection), int(ef_construction), len(name), name, int(max_elements),
+                                 int(max_layer))
+        if not self._h:
+            raise HnswError("new_hnsw_f32 failed: " + last_error())
+        self.dist_name = dist_name
+        self.max_nb_connection = int(max_nb_connection)
+        self.ef_construction = int(ef_construction)
+
+    # ---- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.drop_hnsw_f32(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, r):
+        if r != 0:
+            raise HnswError(last_error())
+
+    # ---- getters / setters (hnsw.rs:810-905)
+    def get_nb_point(self):
+        return int(self._L.hnsw_b200_get_nb_point(self._h))
+
+    def get_max_level_observed(self):
+        return int(self._L.hnsw_b200_get_max_level_observed(self._h))
+
+    def get_max_nb_connection(self):
+        return self.max_nb_connection
+
+    def get_ef_construction(self):
+        return self.ef_construction
+
+    def get_data_dimension(self):
+        return int(self._L.hnsw_b200_get_dim(self._h))
+
+    def set_extend_candidates(self, flag):
+        self._chk(self._L.hnsw_b200_set_extend_candidates(self._h, int(bool(flag))))
+
+    def set_keeping_pruned(self, flag):
+        self._chk(self._L.hnsw_b200_set_keeping_pruned(self._h, int(bool(flag))))
+
+    def set_searching_mode(self, flag):
+        self._chk(self._L.hnsw_b200_set_searching_mode(self._h, int(bool(flag))))
+
+    def modify_level_scale(self, scale):
+        self._chk(self._L.hnsw_b200_modify_level_scale(self._h, float(scale)))
+
+    def set_level_seed(self, seed):
+        self._chk(self._L.hnsw_b200_set_level_seed(self._h, int(seed)))
+
+    def set_insert_batching(self, ratio, max_batch):
+        self._chk(self._L.hnsw_b200_set_insert_batching(self._h, int(ratio), int(max_batch)))
+
+    # ---- insertion (hnsw.rs:1069-1071, 1224-1238; api.rs:47-56)
+    def insert(self, data_with_id):
+        v, i = data_with_id
+        v = np.ascontiguousarray(v, np.float32)
+        before = self.get_nb_point()
+        self._L.insert_f32(self._h, v.size, _p(v), int(i))
+        if self.get_nb_point() != before + 1:
+            raise HnswError("insert_f32 failed: " + last_error())
+
+    insert_data = lambda self, data, id_: self.insert((data, id_))  # AnnT::insert_data
+
+    def parallel_insert(self, datas):
+        """datas: sequence of (vector, id) — goes through parallel_insert_f32 (row pointers)."""
+        if len(datas) == 0:
+            return
+        rows = [np.ascontiguousarray(v, np.float32) for v, _ in datas]
+        d = rows[0].size
+        ptrs = (C.c_void_p * len(rows))(*[r.ctypes.data for r in rows])
+        ids = (C.c_size_t * len(rows))(*[int(i) for _, i in datas])
+        before = self.get_nb_point()
+        self._L.parallel_insert_f32(self._h, len(rows), d, ptrs, ids)
+        if self.get_nb_point() != before + len(rows):
+            raise HnswError("parallel_insert_f32 failed: " + last_error())
+
+    parallel_insert_slice = parallel_insert
+    parallel_insert_data = parallel_insert  # AnnT::parallel_insert_data
+
+    def insert_flat(self, vecs, ids=None, levels=None):
+        """Extension: one flat [n, d] array (no per-row pointers)."""
+        vecs = np.ascontiguousarray(vecs, np.float32)
+        n, d = vecs.shape
+        ids_a = None if ids is None else np.ascontiguousarray(ids, np.uint64)
+        lv = None if levels is None else np.ascontiguousarray(levels, np.int32)
+        self._chk(self._L.hnsw_b200_insert_flat(self._h, _p(vecs), n, d, _p(ids_a), _p(lv)))
+
+    # ---- search (hnsw.rs:1487-1635; api.rs:51-65)
+    def search(self, data, knbn, ef_arg):
+        return self.search_filter(data, knbn, ef_arg, None)
+
+    search_neighbours = search  # AnnT::search_neighbours
+
+    def search_possible_filter(self, data, knbn, ef_arg, filter=None):
+        return self.search_filter(data, knbn, ef_arg, filter)
+
+    def search_filter(self, data, knbn, ef_arg, filter=None):
+        """filter: None | sorted sequence of ids (FilterT for Vec<usize>) | callable(id)->bool."""
+        if filter is None:
+            v = np.ascontiguousarray(data, np.float32)
+            res = self._L.search_neighbours_f32(self._h, v.size, _p(v), int(knbn), int(ef_arg))
+            if not res:
+                raise HnswError("search_neighbours_f32 failed: " + last_error())
+            n = res.contents.nbgh
+            ids = [int(res.contents.neighbours[j].id) for j in range(n)]
+            ds = [float(res.contents.neighbours[j].d) for j in range(n)]
+            self._L.hnsw_b200_free_neighbourhood(res)
+            # p_id needs the extension call; fetch lazily through search_flat when asked for
+            return [Neighbour(i, d, None) for i, d in zip(ids, ds)]
+        o, d, it, pid, cnt = self.search_flat(np.asarray(data, np.float32)[None, :], knbn, ef_arg, filter=filter)
+        return [Neighbour(int(o[0, j]), float(d[0, j]), (int(pid[0, j, 0]), int(pid[0, j, 1]))) for j in range(cnt[0])]
+
+    def parallel_search(self, datas, knbn, ef):
+        """Vec<Vec<Neighbour>> in input order, through parallel_search_neighbours_f32 (row pointers)."""
+        rows = [np.ascontiguousarray(v, np.float32) for v in datas]
+        if not rows:
+            return []
+        ptrs = (C.c_void_p * len(rows))(*[r.ctypes.data for r in rows])
+        res = self._L.parallel_search_neighbours_f32(self._h, len(rows), rows[0].size, ptrs, int(knbn), int(ef))
+        if not res:
+            raise HnswError("parallel_search_neighbours_f32 failed: " + last_error())
+        out = []
+        for i in range(res.contents.len):
+            nb = res.contents.ptr[i]
+            out.append([Neighbour(int(nb.neighbours[j].id), float(nb.neighbours[j].d), None) for j in range(nb.nbgh)])
+        self._L.hnsw_b200_free_vec_api(res)
+        return out
+
+    parallel_search_neighbours = parallel_search  # AnnT::parallel_search_neighbours
+
+    def search_flat(self, queries, knbn, ef, filter=None):
+        """Extension: flat batch.  Returns (origin u64[nq,k], dist f32[nq,k], internal u32[nq,k], pid i32[nq,k,2], counts)."""
+        q = np.ascontiguousarray(queries, np.float32)
+        nq, d = q.shape
+        o = np.empty((nq, knbn), np.uint64)
+        ds = np.empty((nq, knbn), np.float32)
+        it = np.empty((nq, knbn), np.uint32)
+        pid = np.empty((nq, knbn, 2), np.int32)
+        cnt = np.zeros(nq, np.int32)
+        mode, fids, nf, cb = 0, None, 0, FILTER_FN(0)
+        if filter is not None:
+            if callable(filter):
+                mode = 2
+                cb = FILTER_FN(lambda i, _c: 1 if filter(int(i)) else 0)
+            else:
+                mode = 1
+                fids = np.ascontiguousarray(np.sort(np.asarray(filter, np.uint64)))
+                nf = len(fids)
+        self._chk(self._L.hnsw_b200_search_flat(self._h, _p(q), nq, d, int(knbn), int(ef), mode, _p(fids), nf, cb, None,
+                                                _p(o), _p(ds), _p(it), _p(pid), _p(cnt)))
+        return o, ds, it, pid, cnt
+
+    def file_dump(self, path, basename):
+        name = basename.encode()
+        r = self._L.file_dump_f32(self._h, len(name), name)
+        if r != 1:
+            raise HnswError("file_dump_f32 failed: " + last_error())
+        return basename
+
+    # ---- statistics / graph transfer (extensions)
+    def enable_stats(self, on=True):
+        self._chk(self._L.hnsw_b200_enable_stats(self._h, int(on)))
+
+    def get_stats(self, reset=True):
+        out = np.zeros(4, np.uint64)
+        self._chk(self._L.hnsw_b200_get_stats(self._h, _p(out), int(reset)))
+        return {"evals": int(out[0]), "expansions": int(out[1]), "adj_read": int(out[2]), "queries": int(out[3])}
+
+    def export_points(self):
+        n = self.get_nb_point()
+        lv, rk, og = np.empty(n, np.uint8), np.empty(n, np.int32), np.empty(n, np.uint64)
+        e = C.c_int64(-1)
+        self._chk(self._L.hnsw_b200_export_points(self._h, _p(lv), _p(rk), _p(og), C.byref(e)))
+        return lv, rk, og, int(e.value)
+
+    def export_vectors(self):
+        out = np.empty((self.get_nb_point(), self.get_data_dimension()), np.float32)
+        self._chk(self._L.hnsw_b200_export_vectors(self._h, _p(out)))
+        return out
+
+    def export_layer(self, layer):
+        n = self.get_nb_point()
+        ne = int(self._L.hnsw_b200_layer_edges(self._h, layer))
+        if ne < 0:
+            raise HnswError(last_error())
+        off, ids, ds = np.empty(n + 1, np.uint64), np.empty(ne, np.uint32), np.empty(ne, np.float32)
+        self._chk(self._L.hnsw_b200_export_layer(self._h, layer, _p(off), _p(ids), _p(ds)))
+        return off, ids, ds
+
+    def import_graph(self, vecs, origin, levels, entry, layers):
+        """layers: list (index = layer) of (offsets u64[N+1], ids u32[], dists f32[]|None)."""
+        vecs = np.ascontiguousarray(vecs, np.float32)
+        n, d = vecs.shape
+        origin = np.ascontiguousarray(origin, np.uint64)
+        levels = np.ascontiguousarray(levels, np.uint8)
+        keep = []
+        nl = len(layers)
+        offs, idss, dss = (C.c_void_p * nl)(), (C.c_void_p * nl)(), (C.c_void_p * nl)()
+        for l, (off, ids, ds) in enumerate(layers):
+            off = np.ascontiguousarray(off, np.uint64)
+            ids = np.ascontiguousarray(ids, np.uint32)
+            ds = None if ds is None else np.ascontiguousarray(ds, np.float32)
+            keep += [off, ids, ds]
+            offs[l], idss[l] = off.ctypes.data, ids.ctypes.data
+            dss[l] = None if ds is None else ds.ctypes.data
+        self._chk(self._L.hnsw_b200_import_graph(self._h, _p(vecs), n, d, _p(origin), _p(levels), int(entry), nl, offs,
+                                                 idss, dss))
+
+    def dist_batch(self, queries, cand):
+        q = np.ascontiguousarray(queries, np.float32)
+        c = np.ascontiguousarray(cand, np.uint32)
+        out = np.empty(c.shape, np.float32)
+        self._chk(self._L.hnsw_b200_dist_batch(self._h, _p(q), q.shape[0], q.shape[1], _p(c), c.shape[1], _p(out)))
+        return out
+
+    def bruteforce(self, queries, k):
+        q = np.ascontiguousarray(queries, np.float32)
+        ids = np.empty((q.shape[0], k), np.uint32)
+        ds = np.empty((q.shape[0], k), np.float32)
+        self._chk(self._L.hnsw_b200_bruteforce(self._h, _p(q), q.shape[0], q.shape[1], k, _p(ids), _p(ds)))
+        return ids, ds

@@ -1,0 +1,174 @@
+/* libhnsw_b200.so — C ABI of the B200-native HNSW search/insert engine.
+ *
+ * Part 1 re-exports, with identical names, argument order and #[repr(C)] struct layouts, the
+ * extern "C" surface the reference crate (jean-pierreBoth/hnswlib-rs) defines in
+ * /root/reference/src/libext.rs, for the f32 instantiation (the hot path named by
+ * BASELINE.json).  A caller of the reference cdylib (Julia's HnswAnn.jl, C, or the Rust shim in
+ * hnswlib-rs_b200/rust_shim/) can link this library instead.
+ * Part 2 are `hnsw_b200_*` extensions: explicit frees (the reference leaks its answers to the
+ * caller and exports no free, libext.rs:194-200,236-251), flat-array batch calls, options,
+ * graph import/export, filter upload, stand-alone distance / brute-force kernels, statistics.
+ *
+ * No torch types, plain pointers and sizes only.  Every call needing the GPU fails loudly (NULL /
+ * negative status + hnsw_b200_last_error()) when no CUDA device is usable; there is no CPU fallback.
+ */
+#ifndef HNSW_B200_H
+#define HNSW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ Part 1: reference symbols */
+
+/* opaque handle; libext.rs:38-50,100 (declare_myapi_type!(HnswApif32, f32)) */
+typedef struct HnswApif32 HnswApif32;
+
+/* libext.rs:64-71   #[repr(C)] pub struct Neighbour_api { id: usize, d: f32 }   (16 bytes) */
+typedef struct Neighbour_api {
+  size_t id;
+  float d;
+} Neighbour_api;
+
+/* libext.rs:82-87   #[repr(C)] pub struct Neighbourhood_api { nbgh: i64, neighbours: *const Neighbour_api } */
+typedef struct Neighbourhood_api {
+  int64_t nbgh;
+  const Neighbour_api* neighbours;
+} Neighbourhood_api;
+
+/* libext.rs:58-62   #[repr(C)] pub struct Vec_api<T> { len: i64, ptr: *const T }, T = Neighbourhood_api */
+typedef struct Vec_api_Neighbourhood_api {
+  int64_t len;
+  const Neighbourhood_api* ptr;
+} Vec_api_Neighbourhood_api;
+
+/* libext.rs:458-525.  Hnsw::<f32,D>::new(max_nb_conn, 10000, 16, ef_const, D).  cdistname is NOT
+ * NUL-terminated (namelen bytes).  Accepted: "DistL1" "DistL2" "DistDot" "DistHellinger"
+ * "DistJeffreys" "DistJensenShannon" as upstream, plus "DistCosine" (upstream reaches it only
+ * through load_hnswdump_f32_DistCosine).  Unknown name or no usable GPU => NULL. */
+const HnswApif32* init_hnsw_f32(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname);
+
+/* libext.rs:532-620 */
+const HnswApif32* new_hnsw_f32(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname,
+                               size_t max_elements, size_t max_layer);
+
+/* libext.rs:626-630 */
+void drop_hnsw_f32(const HnswApif32* p);
+
+/* libext.rs:643-655.  A host function pointer cannot be evaluated inside a kernel; this entry
+ * point exists for link compatibility and always returns NULL. */
+const HnswApif32* init_hnsw_ptrdist_f32(size_t max_nb_conn, size_t ef_const,
+                                        float (*c_func)(const float*, const float*, unsigned long long));
+
+/* libext.rs:661-677.  The vector is copied; `len` fixes the index dimension on first use and must
+ * match afterwards (the flat point store needs one dimension; mismatches are ignored with an error
+ * recorded in hnsw_b200_last_error()). */
+void insert_f32(HnswApif32* hnsw_api, size_t len, const float* data, size_t id);
+
+/* libext.rs:683-722 */
+void parallel_insert_f32(HnswApif32* hnsw_api, size_t nb_vec, size_t vec_len, const float** datas, const size_t* ids);
+
+/* libext.rs:728-767.  Result is owned by the caller; release with hnsw_b200_free_neighbourhood(). */
+const Neighbourhood_api* search_neighbours_f32(const HnswApif32* hnsw_api, size_t len, const float* data, size_t knbn,
+                                               size_t ef_search);
+
+/* libext.rs:205-254 (instantiated :770).  Answers in input order.  Release with hnsw_b200_free_vec_api(). */
+const Vec_api_Neighbourhood_api* parallel_search_neighbours_f32(const HnswApif32* hnsw_api, size_t nb_vec,
+                                                                int64_t vec_len, const float** data, size_t knbn,
+                                                                size_t ef_search);
+
+/* libext.rs:257-275 (instantiated :771).  Returns 1 on success, -1 on failure. */
+int64_t file_dump_f32(const HnswApif32* hnsw_api, size_t namelen, const uint8_t* filename);
+
+/* libext.rs:1238-1240.  No-op here (diagnostics go through hnsw_b200_last_error). */
+void init_rust_log(void);
+
+/* ------------------------------------------------------------------ Part 2: extensions */
+
+const char* hnsw_b200_last_error(void);
+int hnsw_b200_device_count(void);
+/* select the CUDA device used by handles created afterwards on this thread's process (default 0) */
+int hnsw_b200_set_device(int device);
+
+void hnsw_b200_free_neighbourhood(const Neighbourhood_api* p);
+void hnsw_b200_free_vec_api(const Vec_api_Neighbourhood_api* p);
+
+/* Hnsw setters/getters, /root/reference/src/hnsw.rs:810-905 */
+int hnsw_b200_set_extend_candidates(HnswApif32* h, int flag);  /* hnsw.rs:858 */
+int hnsw_b200_set_keeping_pruned(HnswApif32* h, int flag);     /* hnsw.rs:845 */
+int hnsw_b200_modify_level_scale(HnswApif32* h, double scale); /* hnsw.rs:876-905, scale in [0.2,1] */
+int hnsw_b200_set_searching_mode(HnswApif32* h, int flag);     /* hnsw.rs:834 */
+int hnsw_b200_set_level_seed(HnswApif32* h, uint64_t seed);
+uint64_t hnsw_b200_get_nb_point(const HnswApif32* h);          /* hnsw.rs:810 */
+int hnsw_b200_get_max_level_observed(const HnswApif32* h);     /* hnsw.rs:474 */
+int hnsw_b200_get_dim(const HnswApif32* h);
+/* max in-flight inserts of one GPU batch = clamp(nb_point / ratio, 1, max_batch) (DESIGN.md "batched insert") */
+int hnsw_b200_set_insert_batching(HnswApif32* h, uint32_t ratio, uint32_t max_batch);
+
+/* Flat batched insert: vecs[n][dim] row-major host memory, ids[n] (may be NULL => running index),
+ * levels[n] (may be NULL => drawn from the reference's level law, hnsw.rs:363-374). 0 on success. */
+int hnsw_b200_insert_flat(HnswApif32* h, const float* vecs, uint64_t n, uint64_t dim, const uint64_t* ids,
+                          const int32_t* levels);
+
+/* Flat batched search.  queries[nq][dim] host memory (pinned memory is used directly).
+ * Outputs, each [nq][knbn] except counts[nq]; any of out_internal/out_pid may be NULL:
+ *   out_ids  = origin ids (DataId), out_dist = distances (ascending), missing slots = ~0 / +inf
+ *   out_internal = internal ids, out_pid = PointId (level, rank) pairs as int32[nq][knbn][2]
+ * Filter (FilterT, /root/reference/src/filter.rs:7-24): filter_mode 0 none, 1 sorted origin-id
+ * list (filter_ids / nfilter), 2 predicate callback evaluated ONCE per stored origin id on the
+ * host and materialised to a device bitmap.  0 on success. */
+typedef int (*hnsw_b200_filter_fn)(uint64_t origin_id, void* ctx);
+int hnsw_b200_search_flat(const HnswApif32* h, const float* queries, uint64_t nq, uint64_t dim, uint64_t knbn,
+                          uint64_t ef_search, int filter_mode, const uint64_t* filter_ids, uint64_t nfilter,
+                          hnsw_b200_filter_fn fn, void* ctx, uint64_t* out_ids, float* out_dist,
+                          uint32_t* out_internal, int32_t* out_pid, int32_t* out_counts);
+
+/* Device-resident variant (kernel-only timing, multi-GPU sharding): d_queries [nq][dim] floats and
+ * d_out (Neighbour_api[nq][knbn], internal id in the tail padding) / d_counts (int32[nq]) are
+ * DEVICE pointers owned by the caller; the call enqueues on the index stream and returns without
+ * synchronising unless sync != 0.  kernel_ms (may be NULL) receives the CUDA-event duration of the
+ * search kernel when sync != 0. */
+int hnsw_b200_search_device(const HnswApif32* h, const float* d_queries, uint64_t nq, uint64_t knbn,
+                            uint64_t ef_search, void* d_out, int32_t* d_counts, int sync, float* kernel_ms);
+
+/* Traversal statistics of all searches since the last reset (device counters):
+ * out[0] distance evaluations, out[1] expansions, out[2] adjacency ids read, out[3] queries.
+ * Collection is off by default; enable != 0 turns it on. */
+int hnsw_b200_enable_stats(HnswApif32* h, int enable);
+int hnsw_b200_get_stats(const HnswApif32* h, uint64_t* out4, int reset);
+
+/* Graph export / import as flat arrays (parity tests, NCCL broadcast, dump writer).
+ * Layers are CSR: offsets[nb_point+1], ids[], dists[] (distance to the list owner). */
+int hnsw_b200_export_points(const HnswApif32* h, uint8_t* levels, int32_t* ranks, uint64_t* origin, int64_t* entry);
+int hnsw_b200_export_vectors(const HnswApif32* h, float* out /* [nb_point][dim] */);
+int64_t hnsw_b200_layer_edges(const HnswApif32* h, int layer);
+int hnsw_b200_export_layer(const HnswApif32* h, int layer, uint64_t* offsets, uint32_t* ids, float* dists);
+/* import into an EMPTY handle: nlayers CSR layers (layer l at offsets[l], ids[l], dists[l]; dists[l] may be NULL) */
+int hnsw_b200_import_graph(HnswApif32* h, const float* vecs, uint64_t n, uint64_t dim, const uint64_t* origin,
+                           const uint8_t* levels, int64_t entry, int nlayers, const uint64_t* const* offsets,
+                           const uint32_t* const* ids, const float* const* dists);
+
+/* Frozen-index blobs in device memory, for replication over NCCL (one rank builds, the others
+ * allocate with hnsw_b200_blob_alloc from the broadcast header, then broadcast every blob).
+ * header: 16 x uint64 (see DESIGN.md "replication header"). */
+int hnsw_b200_blob_header(const HnswApif32* h, uint64_t* header16);
+int hnsw_b200_blob_alloc(HnswApif32* h, const uint64_t* header16);
+int hnsw_b200_blob_count(const HnswApif32* h);
+int hnsw_b200_blob_info(const HnswApif32* h, int i, void** dev_ptr, uint64_t* nbytes);
+int hnsw_b200_blob_commit(HnswApif32* h); /* after the broadcasts: pull the small host mirrors back */
+
+/* Stand-alone kernels.  dist_batch: out[nq][m] = dist(queries[i], base[cand[i][j]]) on the index's
+ * point store (host pointers).  bruteforce: exact k nearest (ascending) of each query over the
+ * index's point store: out_ids are INTERNAL ids. */
+int hnsw_b200_dist_batch(const HnswApif32* h, const float* queries, uint64_t nq, uint64_t dim, const uint32_t* cand,
+                         uint64_t m, float* out);
+int hnsw_b200_bruteforce(const HnswApif32* h, const float* queries, uint64_t nq, uint64_t dim, uint64_t k,
+                         uint32_t* out_ids, float* out_dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HNSW_B200_H */

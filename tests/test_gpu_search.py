@@ -1,0 +1,129 @@
+"""GPU parity, search path: libhnsw_b200.so (through the C ABI) vs the CPU oracle on the SAME graph.
+
+The oracle runs in MODE_DET with ORDER_GPU distances, i.e. the total order (dist, id) and the
+summation order the kernels implement, so ids AND distances must be bit-identical, and the
+traversal counters (distance evaluations, expansions, adjacency ids read) must be equal.
+MODE_STD / ORDER_REF (the literal reference behaviour) is compared with the tolerances
+BASELINE.json names: recall@k within 1e-3, distances within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+
+from util import gpu_layers, oracle_layers, recall_ids
+
+pytestmark = pytest.mark.gpu
+
+
+def build_pair(pkg, po, n, d, M, efc, metric, kind="uniform", max_layer=16, seed=1):
+    X = pkg.datagen.make(kind, n, d, seed)
+    o = po.Oracle(M, n, max_layer, efc, metric, d, mode=po.MODE_DET, order=po.ORDER_GPU)
+    o.insert_batch(X)
+    lv, rk, og = o.export_points()
+    h = pkg.Hnsw(M, n, max_layer, efc, metric)
+    h.import_graph(X, og, lv, o.entry, oracle_layers(o))
+    return X, o, h
+
+
+CASES = [
+    # n, d, M, ef_c, metric, data kind, k, ef
+    (10000, 25, 16, 200, "DistL2", "uniform", 10, 24),     # BASELINE.json configs[0] (random.rs shape)
+    (4000, 128, 16, 100, "DistL2", "clustered", 10, 64),   # SIFT shape, small
+    (3000, 25, 24, 100, "DistDot", "unit", 10, 128),       # GloVe shape (angular = DistDot on unit vectors)
+    (3000, 25, 24, 100, "DistCosine", "clustered", 10, 64),
+    (1500, 784, 32, 100, "DistL2", "uniform", 10, 200),    # MNIST shape: wide rows, generic-d kernel
+    (2000, 10, 32, 128, "DistL1", "uniform", 16, 1024),    # tests/equality.rs shape: k=16, ef=1024
+    (2000, 70, 8, 60, "DistL2", "uniform", 5, 5),          # d_pad=96 (generic path), ef == k
+]
+
+
+@pytest.mark.parametrize("n,d,M,efc,metric,kind,k,ef", CASES)
+def test_search_matches_det_oracle_bit_exact(pkg, po, n, d, M, efc, metric, kind, k, ef):
+    X, o, h = build_pair(pkg, po, n, d, M, efc, metric, kind)
+    Q = pkg.datagen.make(kind, 500, d, 2)
+    o.counters()
+    oo, od, oi, opid, oc = o.search_batch(Q, k, ef)
+    cnt_o = o.counters()
+    h.enable_stats(True)
+    go, gd, gi, gpid, gc = h.search_flat(Q, k, ef)
+    cnt_g = h.get_stats()
+    assert np.array_equal(gc, oc)
+    assert np.array_equal(gi, oi), "internal ids differ from the MODE_DET oracle"
+    assert np.array_equal(go, oo)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32)), "distances are not bit-identical"
+    assert np.array_equal(gpid, opid)
+    for key in ("evals", "expansions", "adj_read"):
+        assert cnt_g[key] == cnt_o[key], (key, cnt_g, cnt_o)
+
+
+def test_std_reference_mode_within_tolerance(pkg, po):
+    """literal reference behaviour (Rust-std heaps, AVX2-shaped sums) vs GPU: recall 1e-3, distance 1e-5 rel."""
+    n, d, M, efc, k, ef = 10000, 25, 16, 200, 10, 24
+    X, o, h = build_pair(pkg, po, n, d, M, efc, "DistL2")
+    Q = pkg.datagen.uniform(1000, d, 2)
+    o.set_mode(po.MODE_STD)
+    o.set_order(po.ORDER_REF)
+    oo, od, oi, _, oc = o.search_batch(Q, k, ef)
+    go, gd, gi, _, gc = h.search_flat(Q, k, ef)
+    ti, td = po.bruteforce(X, Q, k, "DistL2")
+    r_o, r_g = recall_ids(oi, oc, ti), recall_ids(gi, gc, ti)
+    assert abs(r_o - r_g) <= 1e-3, (r_o, r_g)
+    same = (oi == gi)
+    assert same.mean() > 0.999
+    rel = np.abs(od[same] - gd[same]) / np.maximum(np.abs(od[same]), 1e-30)
+    assert rel.max() <= 1e-5
+
+
+def test_c_abi_reference_entry_points(pkg, po):
+    """search_neighbours_f32 / parallel_search_neighbours_f32 (row pointers, leaked-answer structs): answers in
+    input order (hnsw.rs:1622-1633) and equal to the flat call."""
+    X, o, h = build_pair(pkg, po, 3000, 16, 12, 64, "DistL2")
+    Q = pkg.datagen.uniform(100, 16, 5)
+    go, gd, gi, _, gc = h.search_flat(Q, 7, 32)
+    par = h.parallel_search([q for q in Q], 7, 32)
+    assert len(par) == len(Q)
+    for i, nb in enumerate(par):
+        assert [x.d_id for x in nb] == go[i, :gc[i]].tolist()
+        assert np.array_equal(np.array([x.distance for x in nb], np.float32), gd[i, :gc[i]])
+    one = h.search(Q[3], 7, 32)
+    assert [x.d_id for x in one] == go[3, :gc[3]].tolist()
+
+
+def test_self_query_distance_zero_and_small_index(pkg, po):
+    """reference asserts: a stored point queried with itself comes back at distance 0
+    (hnsw.rs:1871-1879, hnswio.rs:1639-1640); k larger than the index returns what exists."""
+    X, o, h = build_pair(pkg, po, 300, 12, 8, 40, "DistL1")
+    go, gd, gi, _, gc = h.search_flat(X[:50], 3, 40)
+    assert np.all(gd[:, 0] == 0.0)
+    assert np.array_equal(go[:, 0], np.arange(50, dtype=np.uint64))
+    X2, o2, h2 = build_pair(pkg, po, 5, 4, 8, 40, "DistL2")
+    go, gd, gi, _, gc = h2.search_flat(X2[:2], 10, 16)
+    oo, od, oi, _, oc = o2.search_batch(X2[:2], 10, 16)
+    assert np.array_equal(gc, oc) and gc.max() <= 5
+    assert np.array_equal(gi, oi)
+
+
+def test_empty_index_and_errors(pkg):
+    h = pkg.Hnsw(16, 100, 16, 50, "DistL2")
+    o, d, it, pid, cnt = h.search_flat(np.zeros((3, 8), np.float32), 4, 16)
+    assert np.all(cnt == 0)  # hnsw.rs:1498-1500
+    with pytest.raises(pkg.HnswError):
+        pkg.Hnsw(16, 100, 16, 50, "DistNope")
+    L = pkg.load_library()
+    assert not L.init_hnsw_ptrdist_f32(16, 50, None)
+
+
+def test_dist_batch_and_bruteforce_kernels(pkg, po):
+    X, o, h = build_pair(pkg, po, 2000, 128, 8, 40, "DistL2", "clustered")
+    Q = pkg.datagen.clustered(64, 128, 9)
+    cand = np.random.default_rng(3).integers(0, 2000, (64, 50)).astype(np.uint32)
+    got = h.dist_batch(Q, cand)
+    for i in (0, 7, 63):
+        for j in (0, 13, 49):
+            ref = po.dist(Q[i], X[cand[i, j]], "DistL2", po.ORDER_GPU)
+            assert got[i, j] == np.float32(ref)
+            ref2 = po.dist(Q[i], X[cand[i, j]], "DistL2", po.ORDER_REF)
+            assert abs(got[i, j] - ref2) <= 1e-5 * abs(ref2)
+    bi, bd = h.bruteforce(Q, 10)
+    ti, td = po.bruteforce(X, Q, 10, "DistL2", po.ORDER_GPU)
+    assert np.array_equal(bi, ti)
+    assert np.array_equal(bd.view(np.uint32), td.view(np.uint32))

@@ -299,6 +299,17 @@ int hnsw_b200_search_device(const HnswApif32* h, const float* d_queries, uint64_
                                     kernel_ms));
 }
 
+int hnsw_b200_set_stream(HnswApif32* h, void* cuda_stream) {
+  HB_H(h);
+  return pass(ix, ix->set_stream((cudaStream_t)cuda_stream));
+}
+int hnsw_b200_check_status(HnswApif32* h) {
+  HB_H(h);
+  int r = ix->check_status();
+  if (r < 0) g_err = ix->err();
+  return r;
+}
+
 int hnsw_b200_enable_stats(HnswApif32* h, int enable) {
   HB_H(h);
   return ix->enable_stats(enable != 0);

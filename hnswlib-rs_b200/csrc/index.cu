@@ -61,6 +61,7 @@ Index::Index(int M_, size_t max_elements_, int max_layer_, int ef_c_, int metric
     err_ = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
     return;
   }
+  own_stream_ = stream_;
   sm_count_ = prop.multiProcessorCount;
   if ((e = cudaMalloc(&d_counter_, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&d_status_, sizeof(int))) != cudaSuccess ||
       (e = cudaMalloc(&d_stats_, 4 * sizeof(unsigned long long))) != cudaSuccess) {
@@ -81,7 +82,7 @@ Index::~Index() {
   if (h_pin_) cudaFreeHost(h_pin_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
-  if (stream_) cudaStreamDestroy(stream_);
+  if (own_stream_) cudaStreamDestroy(own_stream_);
 }
 
 template <class T>
@@ -660,6 +661,22 @@ int Index::export_vectors(float* out) const {
   cudaSetDevice(device);
   HB_CUDA(cudaMemcpy2D(out, (size_t)dim * 4, d_vec_.p, (size_t)d_pad * 4, (size_t)dim * 4, n, cudaMemcpyDeviceToHost));
   return 0;
+}
+
+int Index::set_stream(cudaStream_t s) {
+  HB_CUDA(cudaSetDevice(device));
+  HB_CUDA(cudaStreamSynchronize(stream_));
+  stream_ = s ? s : own_stream_;
+  return 0;
+}
+
+int Index::check_status() {
+  HB_CUDA(cudaSetDevice(device));
+  int status = 0;
+  HB_CUDA(cudaMemcpyAsync(&status, d_status_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  HB_CUDA(cudaStreamSynchronize(stream_));
+  if (status) HB_CUDA(cudaMemset(d_status_, 0, sizeof(int)));
+  return status ? 1 : 0;
 }
 
 int Index::enable_stats(bool on) {

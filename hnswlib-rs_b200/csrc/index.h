@@ -93,6 +93,8 @@ class Index {
   const std::string& err() const { return err_; }
   GraphView view() const;
   cudaStream_t stream() const { return stream_; }
+  int set_stream(cudaStream_t s);   // run on a caller-owned stream (e.g. torch's current stream); nullptr = own stream
+  int check_status();               // synchronise; 0 ok, 1 = a visited table overflowed since the last check
   mutable std::mutex mu;  // the C ABI allows calls from many host threads (hnsw.rs:830-833)
 
  private:
@@ -109,7 +111,7 @@ class Index {
 
   bool ok_ = false;
   mutable std::string err_;
-  cudaStream_t stream_ = nullptr;
+  cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   int sm_count_ = 0;
 

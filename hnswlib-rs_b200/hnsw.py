@@ -76,6 +76,8 @@ def load_library():
     L.hnsw_b200_search_flat.argtypes = [vp, vp, u64, u64, u64, u64, i32, vp, u64, FILTER_FN, vp, vp, vp, vp, vp, vp]
     L.hnsw_b200_search_device.argtypes = [vp, vp, u64, u64, u64, vp, vp, i32, vp]
     L.hnsw_b200_get_stats.argtypes = [vp, vp, i32]
+    L.hnsw_b200_set_stream.argtypes = [vp, vp]
+    L.hnsw_b200_check_status.argtypes = [vp]
     L.hnsw_b200_export_points.argtypes = [vp, vp, vp, vp, vp]
     L.hnsw_b200_export_vectors.argtypes = [vp, vp]
     L.hnsw_b200_layer_edges.restype = i64
@@ -305,6 +307,45 @@ class Hnsw:
         out = np.zeros(4, np.uint64)
         self._chk(self._L.hnsw_b200_get_stats(self._h, _p(out), int(reset)))
         return {"evals": int(out[0]), "expansions": int(out[1]), "adj_read": int(out[2]), "queries": int(out[3])}
+
+    def set_stream(self, cuda_stream):
+        self._chk(self._L.hnsw_b200_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def check_status(self):
+        r = self._L.hnsw_b200_check_status(self._h)
+        if r < 0:
+            raise HnswError(last_error())
+        return r
+
+    def search_device(self, d_queries_ptr, nq, knbn, ef, d_out_ptr, d_counts_ptr, sync=True):
+        """Device-resident search: raw device pointers in, Neighbour_api[nq][knbn] + int32 counts out.
+        Returns the kernel's CUDA-event time in ms when sync is true."""
+        ms = C.c_float(0.0)
+        self._chk(self._L.hnsw_b200_search_device(self._h, C.c_void_p(d_queries_ptr), nq, int(knbn), int(ef),
+                                                  C.c_void_p(d_out_ptr), C.c_void_p(d_counts_ptr), int(bool(sync)),
+                                                  C.byref(ms) if sync else None))
+        return float(ms.value)
+
+    def blob_header(self):
+        h16 = np.zeros(16, np.uint64)
+        self._chk(self._L.hnsw_b200_blob_header(self._h, _p(h16)))
+        return h16
+
+    def blob_alloc(self, h16):
+        h16 = np.ascontiguousarray(h16, np.uint64)
+        self._chk(self._L.hnsw_b200_blob_alloc(self._h, _p(h16)))
+
+    def blobs(self):
+        """[(device pointer, nbytes)] of the frozen index arrays (replication over NCCL)."""
+        out = []
+        for i in range(self._L.hnsw_b200_blob_count(self._h)):
+            ptr, nb = C.c_void_p(), C.c_uint64()
+            self._chk(self._L.hnsw_b200_blob_info(self._h, i, C.byref(ptr), C.byref(nb)))
+            out.append((ptr.value or 0, int(nb.value)))
+        return out
+
+    def blob_commit(self):
+        self._chk(self._L.hnsw_b200_blob_commit(self._h))
 
     def export_points(self):
         n = self.get_nb_point()

@@ -134,6 +134,13 @@ int hnsw_b200_search_flat(const HnswApif32* h, const float* queries, uint64_t nq
 int hnsw_b200_search_device(const HnswApif32* h, const float* d_queries, uint64_t nq, uint64_t knbn,
                             uint64_t ef_search, void* d_out, int32_t* d_counts, int sync, float* kernel_ms);
 
+/* Run this handle's kernels and copies on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL
+ * restores the handle's own stream), e.g. so that torch.cuda.Event on torch's current stream brackets them. */
+int hnsw_b200_set_stream(HnswApif32* h, void* cuda_stream);
+/* After asynchronous hnsw_b200_search_device calls: synchronise and report 1 if a per-warp visited table
+ * overflowed (those answers are empty; re-run them with sync != 0, which grows the tables), 0 if not, <0 on error. */
+int hnsw_b200_check_status(HnswApif32* h);
+
 /* Traversal statistics of all searches since the last reset (device counters):
  * out[0] distance evaluations, out[1] expansions, out[2] adjacency ids read, out[3] queries.
  * Collection is off by default; enable != 0 turns it on. */

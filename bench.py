@@ -39,8 +39,8 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=1000000)
     ap.add_argument("--d", type=int, default=128)
@@ -216,8 +216,11 @@ def run_ours(a, rank, world, local_rank):
     cnt_dev = torch.empty((a.nq,), dtype=torch.int32, device="cuda")
     gather_dev = torch.empty((world, a.nq, a.k, 16), dtype=torch.uint8, device="cuda") if multi else None
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream()
-    h.set_stream(stream.cuda_stream)   # library kernels now run on torch's current stream
+    # a dedicated (non-default) torch stream: the library's kernels, torch's events and the NCCL collectives all
+    # go through it, so torch.cuda.Event brackets exactly the launches of the timed region
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    h.set_stream(stream.cuda_stream)
 
     def step_device(b, sync=False):
         ms = h.search_device(q_dev[b % NB].data_ptr(), a.nq, a.k, a.ef, out_dev.data_ptr(), cnt_dev.data_ptr(), sync=sync)

@@ -263,7 +263,7 @@ struct Visited {
   uint32_t epoch;
   uint32_t epoch_max;
   uint32_t tag;
-  uint32_t used;  // lane-local count of insertions (summed on demand)
+  uint32_t used;  // insertions of the current search (warp-uniform)
   uint32_t limit;
 
   __device__ __forceinline__ void init(const VisitedCfg& c, uint32_t slot) {
@@ -290,30 +290,48 @@ struct Visited {
     tag = epoch << id_bits;
     used = 0;
   }
-  // per-lane; true when id was not yet in the set (and is now)
-  __device__ __forceinline__ bool test_and_set(uint32_t id) {
+  // Warp-collective test-and-set of up to 32 ids (one per lane, `valid` lanes only).  Returns true in the
+  // lanes whose id was not yet in the set (it is afterwards).  The table is private to this warp, so no
+  // atomics are needed: lanes that find the same free slot in the same round elect the lowest lane
+  // (match_any); the others probe on.  One L2 round trip per round, and almost always one round.
+  __device__ __forceinline__ bool test_and_set(uint32_t id, bool valid) {
     const uint32_t want = tag | id;
     uint32_t h = (id * 2654435761u) >> shift;
-    for (;;) {
-      uint32_t cur = __ldcg(tab + h);
-      if (cur == want) return false;
-      if ((cur >> id_bits) != epoch) {
-        uint32_t old = atomicCAS(tab + h, cur, want);
-        if (old == cur) {
-          used++;
-          return true;
+    bool pending = valid, fresh = false;
+    while (__any_sync(FULL, pending)) {
+      uint32_t cur = 0;
+      if (pending) cur = __ldcg(tab + h);
+      bool claim = false;
+      if (pending) {
+        if (cur == want) {
+          pending = false;  // already visited
+        } else if ((cur >> id_bits) != epoch) {
+          claim = true;  // stale or empty slot
+        } else {
+          h = (h + 1) & mask;
         }
-        if (old == want) return false;
       }
-      h = (h + 1) & mask;
+      const unsigned claimers = __ballot_sync(FULL, claim);
+      if (claim) {
+        const unsigned same = __match_any_sync(claimers, h);
+        const int leader = __ffs(same) - 1;
+        const uint32_t lead_id = __shfl_sync(claimers, id, leader);
+        if (lane_id() == leader) {
+          __stcg(tab + h, want);
+          fresh = true;
+          pending = false;
+        } else if (lead_id == id) {
+          pending = false;  // the same id twice in one chunk: the leader records it
+        } else {
+          h = (h + 1) & mask;
+        }
+      }
+      __syncwarp();  // orders this round's stores before the next round's loads
     }
+    used += __popc(__ballot_sync(FULL, fresh));  // warp-uniform count
+    return fresh;
   }
-  __device__ __forceinline__ bool overflowing() const {
-    uint32_t t = used;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-    return t >= limit;
-  }
+  __device__ __forceinline__ bool overflowing() const { return used >= limit; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -345,6 +363,17 @@ struct SortedQueue {
     for (int base = 0; base < n; base += 32) {
       int i = base + lane;
       bool open = (i < n) && ((w[i] & 1ull) == 0ull);
+      unsigned m = __ballot_sync(FULL, open);
+      if (m) return base + __ffs(m) - 1;
+    }
+    return -1;
+  }
+  // index of the first unexpanded entry at or after `from`, or -1
+  __device__ __forceinline__ int next_unexpanded(int from) const {
+    const int lane = lane_id();
+    for (int base = from & ~31; base < n; base += 32) {
+      int i = base + lane;
+      bool open = (i < n) && (i >= from) && ((w[i] & 1ull) == 0ull);
       unsigned m = __ballot_sync(FULL, open);
       if (m) return base + __ffs(m) - 1;
     }

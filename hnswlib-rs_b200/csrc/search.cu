@@ -8,7 +8,7 @@
 namespace hb {
 
 template <class Op, int CH, int U>
-__global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(SearchParams p) {
+__global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GraphView& g = p.g;

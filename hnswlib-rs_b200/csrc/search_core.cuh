@@ -36,7 +36,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
   __syncwarp();
   st.evals += 1;
   const float d0 = s.cand_d[0];
-  if (lane == 0) vis.test_and_set(ep);  // hnsw.rs:955-956
+  vis.test_and_set(ep, lane == 0);  // hnsw.rs:955-956
   Q.reset(s.wbuf, ef);
   if (lane == 0) s.wbuf[0] = make_key(d0, ep);  // hnsw.rs:958-967 (ep enters W and C)
   Q.n = 1;
@@ -52,11 +52,21 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
     int cap;
     const uint32_t* ids = list_ids(g, c, layer, cap);  // hnsw.rs:1006
     st.expansions += 1;
+    {  // pull the adjacency rows of the two most likely next candidates towards L2 while this one is expanded
+      const int i1 = Q.next_unexpanded(0);
+      const int i2 = i1 >= 0 ? Q.next_unexpanded(i1 + 1) : -1;
+      const int pick = lane == 0 ? i1 : (lane == 1 ? i2 : -1);
+      if (pick >= 0) {
+        int pcap;
+        const uint32_t* pids = list_ids(g, key_id(Q.w[pick]), layer, pcap);
+        if (pids) asm volatile("prefetch.global.L2 [%0];" ::"l"(pids));
+      }
+    }
     for (int base = 0; base < cap; base += 32) {  // hnsw.rs:1013, 32 neighbours at a time
       const uint32_t nid = (base + lane < cap) ? ids[base + lane] : INVALID_ID;
       const unsigned valid = __ballot_sync(FULL, nid != INVALID_ID);
       st.adj += __popc(valid);
-      const bool fresh = (nid != INVALID_ID) && vis.test_and_set(nid);  // hnsw.rs:1016-1017
+      const bool fresh = vis.test_and_set(nid, nid != INVALID_ID);  // hnsw.rs:1016-1017
       const unsigned m = __ballot_sync(FULL, fresh);
       const int cnt = __popc(m);
       if (cnt) {

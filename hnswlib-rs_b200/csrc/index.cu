@@ -78,7 +78,7 @@ Index::~Index() {
   cudaFree(d_vec_.p); cudaFree(d_adj0_.p); cudaFree(d_adjU_.p); cudaFree(d_upoff_.p); cudaFree(d_adj0d_.p);
   cudaFree(d_adjUd_.p); cudaFree(d_level_.p); cudaFree(d_plevel_.p); cudaFree(d_origin_.p); cudaFree(d_locks_.p);
   cudaFree(d_vis_tab_); cudaFree(d_vis_epoch_); cudaFree(d_counter_); cudaFree(d_status_); cudaFree(d_stats_);
-  cudaFree(d_q_); cudaFree(d_out_); cudaFree(d_cnt_); cudaFree(d_fbits_); cudaFree(d_mask_);
+  cudaFree(d_q_); cudaFree(d_out_); cudaFree(d_cnt_); cudaFree(d_fbits_); cudaFree(d_mask_); cudaFree(d_cbuf_);
   if (h_pin_) cudaFreeHost(h_pin_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
@@ -142,6 +142,10 @@ int Index::ensure_upper(size_t need) {
 int Index::ensure_visited(size_t slots, size_t cap_entries) {
   if (slots <= vis_slots_ && cap_entries <= vis_cap_) return 0;
   size_t ns = std::max(slots, vis_slots_), nc = std::max(cap_entries, vis_cap_);
+  if (ns * nc * sizeof(uint32_t) > ((size_t)8 << 30)) {  // do not carry a huge shape over (filtered searches use few, big tables)
+    ns = slots;
+    nc = cap_entries;
+  }
   HB_CUDA(cudaStreamSynchronize(stream_));
   cudaFree(d_vis_tab_);
   cudaFree(d_vis_epoch_);
@@ -488,7 +492,6 @@ int Index::search_device(const float* d_queries, size_t nq, size_t k, size_t ef_
                          NeighbourOut* d_out, int32_t* d_counts, bool sync, float* kernel_ms) {
   if (nq == 0) return 0;
   if (k == 0) return fail("knbn must be positive");
-  if (d_filter_bits) return fail("filtered search kernel not available in this build");
   HB_CUDA(cudaSetDevice(device));
   if (dim == 0) {  // empty index: every answer is empty (hnsw.rs:1498-1503)
     HB_CUDA(cudaMemsetAsync(d_counts, 0, nq * sizeof(int32_t), stream_));
@@ -518,19 +521,36 @@ int Index::search_device(const float* d_queries, size_t nq, size_t k, size_t ef_
   const int wpb = SEARCH_THREADS / 32;
   const size_t smem = spw * wpb;
   if (smem > 220 * 1024) return fail("ef / dimension too large for the search kernel's shared memory");
+  const bool filtered = d_filter_bits != nullptr;
+  p.cbuf = nullptr;
+  p.ccap = 0;
   int bps = 0;
-  HB_CUDA(launch_search(p, metric, 0, smem, stream_, true, &bps));
+  if (filtered) HB_CUDA(launch_search_filtered(p, metric, 0, smem, stream_, true, &bps));
+  else HB_CUDA(launch_search(p, metric, 0, smem, stream_, true, &bps));
   if (bps < 1) return fail("search kernel does not fit on an SM");
-  const int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (nq + wpb - 1) / wpb);
+  int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (nq + wpb - 1) / wpb);
   const int deg = layer0 == 0 ? 2 * M : M;
   size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)2 * (p.ef + 16) * deg));
   for (int attempt = 0;; ++attempt) {
     int r;
+    if (filtered) {
+      // a filtered search keeps expanding until its candidate queue is empty (hnsw.rs:992-1001) and may visit the
+      // whole graph: keep (visited table + candidate queue) under ~6 GB by running fewer warps when tables are big
+      const size_t per_slot = std::max(vcap, vis_cap_) * 12;
+      const size_t max_slots = std::max<size_t>(wpb, ((size_t)6 << 30) / per_slot);
+      grid = (int)std::max<size_t>(1, std::min<size_t>(grid, max_slots / wpb));
+    }
     if ((r = ensure_visited((size_t)grid * wpb, vcap))) return r;
     if ((r = fill_visited_cfg(p.vis))) return r;
+    if (filtered) {
+      if ((r = ensure_scratch(&d_cbuf_, &d_cbuf_bytes_, (size_t)grid * wpb * vis_cap_ * 8))) return r;
+      p.cbuf = (uint64_t*)d_cbuf_;
+      p.ccap = (uint32_t)vis_cap_;
+    }
     HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
     HB_CUDA(cudaEventRecord(ev0_, stream_));
-    HB_CUDA(launch_search(p, metric, grid, smem, stream_, false, nullptr));
+    if (filtered) HB_CUDA(launch_search_filtered(p, metric, grid, smem, stream_, false, nullptr));
+    else HB_CUDA(launch_search(p, metric, grid, smem, stream_, false, nullptr));
     HB_CUDA(cudaEventRecord(ev1_, stream_));
     if (!sync) break;
     int status = 0;
@@ -540,7 +560,7 @@ int Index::search_device(const float* d_queries, size_t nq, size_t k, size_t ef_
       if (kernel_ms) HB_CUDA(cudaEventElapsedTime(kernel_ms, ev0_, ev1_));
       break;
     }
-    if (attempt >= 8) return fail("visited table overflow persists");
+    if (attempt >= 24) return fail("visited table overflow persists");
     HB_CUDA(cudaMemsetAsync(d_status_, 0, sizeof(int), stream_));
     vcap = vis_cap_ * 2;
   }

@@ -148,6 +148,8 @@ class Index {
   size_t d_cnt_bytes_ = 0;
   void* d_fbits_ = nullptr;
   size_t d_fbits_bytes_ = 0;
+  void* d_cbuf_ = nullptr;
+  size_t d_cbuf_bytes_ = 0;
   void* d_mask_ = nullptr;
   size_t d_mask_bytes_ = 0;
 };

@@ -35,6 +35,8 @@ struct SearchParams {
   unsigned long long* stats;    // nullptr or [3]: evals, expansions, adjacency ids read
   int* status;                  // set to 1 on visited-table overflow
   int smem_per_warp;
+  uint64_t* cbuf;  // filtered search only: candidate queue C, [slots][ccap] keys
+  uint32_t ccap;
 };
 
 inline size_t search_smem_per_warp(int d4, int ef) { return (size_t)d4 * 16 + (size_t)ef * 8 + 32 * 8; }
@@ -63,6 +65,8 @@ cudaError_t launch_insert_search(const InsertParams& p, int metric, int grid, si
                                  bool query_only, int* blocks_per_sm);
 cudaError_t launch_insert_link(const InsertParams& p, int grid, cudaStream_t st);
 
+cudaError_t launch_search_filtered(const SearchParams& p, int metric, int grid, size_t smem, cudaStream_t st,
+                                   bool query_only, int* blocks_per_sm);
 cudaError_t launch_search(const SearchParams& p, int metric, int grid, size_t smem, cudaStream_t st, bool query_only,
                           int* blocks_per_sm);
 

@@ -219,6 +219,9 @@ class Index {
     const bool has_filter = filter && filter->active;
     while (!C.empty()) {  // 969
       Item c = C.pop();   // 971
+      // 973 unwraps W.peek(): the reference would PANIC on an empty W here (reachable only with a filter, ef == 1 and
+      // an entry point that fails it); the restatement and the engine return the empty W instead.
+      if (W.empty()) return W;
       const Item& f = W.peek();  // 973
       bool stop;
       if (mode == MODE_STD) stop = (-c.kd) > f.kd;  // 981

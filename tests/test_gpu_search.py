@@ -127,3 +127,33 @@ def test_dist_batch_and_bruteforce_kernels(pkg, po):
     ti, td = po.bruteforce(X, Q, 10, "DistL2", po.ORDER_GPU)
     assert np.array_equal(bi, ti)
     assert np.array_equal(bd.view(np.uint32), td.view(np.uint32))
+
+
+def test_filtered_search_matches_oracle(pkg, po):
+    """search_filter with a FilterT (sorted id list and predicate forms, filter.rs:7-24) vs the oracle's
+    restatement of the filter branches (hnsw.rs:981-1001, 1037-1050, 1549-1563): identical ids/distances;
+    plus the reference's own assertions (tests/filtertest.rs:141,211,258,263-269)."""
+    X, o, h = build_pair(pkg, po, 3000, 16, 8, 100, "DistL2")
+    Q = pkg.datagen.uniform(60, 16, 8)
+    allow = np.arange(0, 3000, 3)
+    oo, od, oi, opid, oc = o.search_batch(Q, 10, 64, filter_ids=allow)
+    go, gd, gi, gpid, gc = h.search_flat(Q, 10, 64, filter=allow)
+    assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    assert np.all(go[gc[:, None] > np.arange(10)[None, :]] % 3 == 0)
+    # predicate form == sorted-list form
+    g2 = h.search_flat(Q, 10, 64, filter=lambda i: i % 3 == 0)
+    assert np.array_equal(g2[2], gi) and np.array_equal(g2[4], gc)
+    # always-false filter => 0 hits; single-admit filter => <= 1 hit, and it is the admitted id
+    z = h.search_flat(Q, 10, 64, filter=lambda i: False)
+    assert np.all(z[4] == 0)
+    one = h.search_flat(Q, 10, 4, filter=[1234])
+    oone = o.search_batch(Q, 10, 4, filter_ids=[1234])
+    assert np.all(one[4] <= 1) and np.array_equal(one[4], oone[4]) and np.array_equal(one[2], oone[2])
+    # ef == 1 with a restrictive filter (the case where the reference's W can run empty)
+    e1 = h.search_flat(Q, 1, 1, filter=allow)
+    o1 = o.search_batch(Q, 1, 1, filter_ids=allow)
+    assert np.array_equal(e1[4], o1[4]) and np.array_equal(e1[2], o1[2])
+    # through the mirrored single-query API
+    res = h.search_filter(Q[0], 10, 64, filter=allow.tolist())
+    assert [r.d_id for r in res] == go[0, :gc[0]].tolist()

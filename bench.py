@@ -168,15 +168,11 @@ def run_reference(a, rank, world):
 
 
 # ------------------------------------------------------------------------------------------- our arm
-class _DevMem:
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
 def run_ours(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     pkg = importlib.import_module("hnswlib-rs_b200")
+    replicate = importlib.import_module("hnswlib-rs_b200.replicate")
     dev = local_rank
     torch.cuda.set_device(dev)
     multi = world > 1
@@ -194,18 +190,7 @@ def run_ours(a, rank, world, local_rank):
     bcast_s = 0.0
     if multi:
         t0 = time.perf_counter()
-        hdr = torch.from_numpy(h.blob_header().astype(np.int64)).cuda() if rank == 0 else torch.zeros(16, dtype=torch.int64, device="cuda")
-        dist.broadcast(hdr, 0)
-        if rank != 0:
-            h.blob_alloc(hdr.cpu().numpy().astype(np.uint64))
-        for ptr, nb in h.blobs():
-            if nb == 0:
-                continue
-            t = torch.as_tensor(_DevMem(ptr, nb), device=f"cuda:{dev}")
-            dist.broadcast(t, 0)                      # ncclBroadcast over NVLink/NVSwitch
-        torch.cuda.synchronize()
-        if rank != 0:
-            h.blob_commit()
+        replicate.broadcast_index(h, 0, f"cuda:{dev}")      # ncclBroadcast of the frozen arrays
         bcast_s = time.perf_counter() - t0
 
     # ---- queries: NB rotating batches per rank, seeded per rank; pinned host copies + device copies
@@ -214,7 +199,7 @@ def run_ours(a, rank, world, local_rank):
     q_dev = [q.cuda(non_blocking=True) for q in q_host]
     out_dev = torch.empty((a.nq, a.k, 16), dtype=torch.uint8, device="cuda")        # Neighbour_api[nq][k]
     cnt_dev = torch.empty((a.nq,), dtype=torch.int32, device="cuda")
-    gather_dev = torch.empty((world, a.nq, a.k, 16), dtype=torch.uint8, device="cuda") if multi else None
+    gather_dev = torch.empty((world * a.nq, a.k, 16), dtype=torch.uint8, device="cuda") if multi else None
     torch.cuda.synchronize()
     # a dedicated (non-default) torch stream: the library's kernels, torch's events and the NCCL collectives all
     # go through it, so torch.cuda.Event brackets exactly the launches of the timed region

@@ -66,6 +66,25 @@ class ClockSampler:
         self.th = None
 
     def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            hd = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(hd, nv.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+            while not self.stop.is_set():
+                sm = nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(hd)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(hd)
+                pw = nv.nvmlDeviceGetPowerUsage(hd) / 1000.0
+                self.rows.append([str(sm), str(mx), str(pw)] + ["Active" if r & bits[k] else "Not Active" for k in
+                                 ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+                self.stop.wait(0.01)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -98,8 +117,9 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        pw = max(float(r[2]) for r in self.rows)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "power_w_max": pw}
 
 
 def measured_peak_gbs():
@@ -262,7 +282,7 @@ def run_ours(a, rank, world, local_rank):
     def step_e2e(b):
         res = h.search_flat(qh_np[b % NB], a.k, a.ef)
         if multi:   # answers to rank 0 (host side, gloo)
-            t = torch.from_numpy(res[0])
+            t = torch.from_numpy(res[0].view(np.int64))   # gloo has no uint64
             gl = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
             dist.gather(t, gl, dst=0, group=gloo)
         return res

@@ -102,9 +102,14 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
       const int n = Q.n;
       const int nb = (l == 0) ? g.deg0 : g.M;  // 1177-1183
       int cnt = 0;
-      if (n <= nb) {
-        // 1318-1327: few candidates, take them all nearest first.  (extend_candidates is handled
-        // by the host: it is only reachable while the index holds <= 2M points.)
+      // extend_candidates (1318-1362, layer 0 only): with |cand| <= nb the reference adds the neighbours of the
+      // candidates that are not candidates themselves, then runs the heuristic instead of taking everything.
+      // When |cand| < ef_construction the search ended because every reachable node was visited, accepted
+      // (|W| < ef) and expanded, so those neighbours are all candidates already and the extension set is
+      // empty; the host only allows the flag when ef_construction > 2*max_nb_connection >= |cand|.
+      const bool heuristic_on_few = p.extend && l == 0;
+      if (n <= nb && !heuristic_on_few) {
+        // 1318-1327: few candidates, take them all nearest first
         for (int i = lane; i < n; i += 32) {
           const uint64_t k = Q.w[i];
           sel_id[i] = key_id(k);

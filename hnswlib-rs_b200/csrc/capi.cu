@@ -213,8 +213,10 @@ void hnsw_b200_free_vec_api(const Vec_api_Neighbourhood_api* p) {
 
 int hnsw_b200_set_extend_candidates(HnswApif32* h, int flag) {
   HB_H(h);
-  if (flag) return set_err("extend_candidates is not supported by the GPU insert path yet");
-  ix->extend_candidates = false;
+  if (flag && ix->ef_c <= 2 * ix->M)
+    return set_err("extend_candidates needs ef_construction > 2*max_nb_connection in this engine (otherwise the "
+                   "extension set of hnsw.rs:1336-1362 is not provably empty)");
+  ix->extend_candidates = flag != 0;
   return 0;
 }
 int hnsw_b200_set_keeping_pruned(HnswApif32* h, int flag) {

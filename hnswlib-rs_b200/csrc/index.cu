@@ -247,6 +247,7 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
   p.layer_mask = reinterpret_cast<const uint16_t*>(d_mask_) + mask_off;
   p.ef_c = ef_c;
   p.keep_pruned = keep_pruned ? 1 : 0;
+  p.extend = extend_candidates ? 1 : 0;
   p.work_counter = d_counter_;
   p.locks = d_locks_.p;
   p.stats = nullptr;

@@ -48,6 +48,7 @@ struct InsertParams {
   const uint16_t* layer_mask;  // [count] bit l set <=> some point of exact level l exists when this point searches
   int ef_c;
   int keep_pruned;
+  int extend;  // extend_candidates flag (hnsw.rs:858), only with ef_c > 2M
   VisitedCfg vis;
   unsigned int* work_counter;
   int* locks;  // [capacity] per-point spin locks (phase B)

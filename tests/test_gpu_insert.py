@@ -80,3 +80,26 @@ def test_reference_entry_points_insert_then_search(pkg, po):
     assert res[0].d_id == 1123 and res[0].distance == 0.0
     par = h.parallel_search([X[5], X[599]], 2, 32)
     assert par[0][0].d_id == 1005 and par[1][0].d_id == 1599
+
+
+@pytest.mark.parametrize("extend,keep_pruned", [(True, False), (False, True), (True, True)])
+def test_serial_gpu_build_options_equal_oracle(pkg, po, extend, keep_pruned):
+    """set_extend_candidates / set_keeping_pruned (hnsw.rs:845-870): serial GPU build == oracle graph."""
+    n, d, M, efc = 1200, 12, 6, 40
+    X = pkg.datagen.uniform(n, d, 21)
+    o = po.Oracle(M, n, 16, efc, "DistL2", d, mode=po.MODE_DET, order=po.ORDER_GPU)
+    o.set_extend_candidates(extend)
+    o.set_keeping_pruned(keep_pruned)
+    levels = o.draw_levels(n)
+    o.insert_batch(X, levels=levels)
+    h = pkg.Hnsw(M, n, 16, efc, "DistL2")
+    h.set_extend_candidates(extend)
+    h.set_keeping_pruned(keep_pruned)
+    h.set_insert_batching(1 << 30, 1)
+    h.insert_flat(X, levels=levels)
+    goff, gids, gds = h.export_layer(0)
+    ooff, oids, ods = o.export_layer(0)
+    assert np.array_equal(goff, ooff) and np.array_equal(gids, oids)
+    assert np.array_equal(gds.view(np.uint32), ods.view(np.uint32))
+    with pytest.raises(pkg.HnswError):
+        pkg.Hnsw(32, 100, 16, 48, "DistL2").set_extend_candidates(True)   # ef_c <= 2M: refused, not ignored

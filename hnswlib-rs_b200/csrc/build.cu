@@ -34,7 +34,9 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
   unsigned char* base = smem_raw + (size_t)warp * p.smem_per_warp;
   // layout: q4 | qe4 | wbuf[ef_c] | cand_id[32] cand_d[32] | sel_id[nbmax] sel_d[nbmax] tmp[nbmax] | disc[ef_c] (u16)
   WarpSmem s;
-  size_t off = 0;
+  size_t off = stage_bytes(g.d4);
+  Stage stg;
+  stg.buf = off ? reinterpret_cast<float4*>(base) : nullptr;
   s.q4 = reinterpret_cast<float4*>(base + off);
   off += (size_t)g.d4 * 16;
   float4* qe4 = reinterpret_cast<float4*>(base + off);
@@ -45,6 +47,11 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
   off += 128;
   s.cand_d = reinterpret_cast<float*>(base + off);
   off += 128;
+  stg.bar = reinterpret_cast<uint64_t*>(base + off);
+  off += 16;
+  stg.phase = 0;
+  if (lane == 0) mbar_init(stg.bar, 1);
+  __syncwarp();
   const int nbmax = g.deg0;
   uint32_t* sel_id = reinterpret_cast<uint32_t*>(base + off);
   off += (size_t)nbmax * 4;
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
     // be traversed (DESIGN.md "lists above a point's level") and is not materialised.
     for (int l = g.entry_level; l > lv; --l) {
       if (!((mask >> l) & 1u)) continue;  // points_by_layer[l].is_empty() => empty result (942-946)
-      search_layer<Op, CH, U>(g, s, vis, Q, cur, 1, l, st, overflow);
+      search_layer<Op, CH, U>(g, s, stg, vis, Q, cur, 1, l, st, overflow);
       if (overflow) break;
       const uint64_t k0 = Q.w[0];
       const float t = key_dist(k0);  // == dist(data, ep) recomputed at 1146
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
     // ---- layers level..0: ef_construction search + selection (hnsw.rs:1158-1205)
     for (int l = lv; l >= 0 && !overflow; --l) {
       if (!((mask >> l) & 1u)) continue;
-      search_layer<Op, CH, U>(g, s, vis, Q, cur, p.ef_c, l, st, overflow);
+      search_layer<Op, CH, U>(g, s, stg, vis, Q, cur, p.ef_c, l, st, overflow);
       if (overflow) break;
       const int n = Q.n;
       const int nb = (l == 0) ? g.deg0 : g.M;  // 1177-1183

@@ -244,6 +244,85 @@ __device__ __forceinline__ void warp_dists(const float4* __restrict__ vec, int d
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA staging: rows copied HBM -> shared memory by the bulk-copy engine (cp.async.bulk, SASS UBLKCP), completion
+// signalled on an mbarrier.  One lane issues one 1-D bulk copy per row, so a row in flight costs no registers.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+
+constexpr int STAGE_ROWS = 8;  // rows of a chunk fetched by TMA; the rest of the chunk goes through registers
+
+struct Stage {
+  float4* buf;    // [STAGE_ROWS][d4] or nullptr (rows too long to stage)
+  uint64_t* bar;  // mbarrier, arrival count 1
+  uint32_t phase;
+};
+
+// Hybrid row fetch: rows [0, min(n,8)) by TMA into shared memory, rows [8, n) through registers (warp_dists),
+// all in flight together; then the staged rows are reduced from shared memory with the same lane/chunk mapping,
+// so every distance is bit-identical to the pure register path.
+template <class Op, int CH, int U>
+__device__ __forceinline__ void warp_dists_staged(const float4* __restrict__ vec, int d4, const float4* q4,
+                                                  const uint32_t* ids, int n, float* out, Stage& st) {
+  if constexpr (CH == 0) {
+    warp_dists<Op, CH, U>(vec, d4, q4, ids, n, out);
+  } else {
+    const int lane = lane_id();
+    const int nst = n < STAGE_ROWS ? n : STAGE_ROWS;
+    const uint32_t row_bytes = (uint32_t)d4 * 16u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the stage precede the async writes
+    if (lane == 0) mbar_expect_tx(st.bar, row_bytes * nst);
+    __syncwarp();
+    if (lane < nst) bulk_g2s(st.buf + (size_t)lane * d4, vec + (size_t)ids[lane] * d4, row_bytes, st.bar);
+    if (n > STAGE_ROWS) warp_dists<Op, CH, U>(vec, d4, q4, ids + STAGE_ROWS, n - STAGE_ROWS, out + STAGE_ROWS);
+    const int g = lane & 7, r = lane >> 3;
+    float4 qv[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) qv[i] = q4[g + 8 * i];
+    mbar_wait(st.bar, st.phase);
+    st.phase ^= 1u;
+#pragma unroll
+    for (int pass = 0; pass < STAGE_ROWS / 4; ++pass) {
+      const int row = pass * 4 + r;
+      if (pass * 4 < nst) {
+        const float4* src = st.buf + (size_t)(row < nst ? row : nst - 1) * d4 + g;
+        typename Op::acc_t a = Op::zero();
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const float4 x = src[8 * i];
+          step4<Op>(a, qv[i], x);
+        }
+        const float dist = reduce8<Op>(a);
+        if (g == 0 && row < nst) out[row] = dist;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Visited set: one open-addressing table per resident warp ("warp slot") in global memory (L2
 // resident).  Entry = (epoch << id_bits) | id; an entry whose epoch differs from the current one is
 // free, so a new search only bumps the epoch instead of clearing.  Exact (no false positives).

@@ -151,10 +151,11 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_filter_kernel(SearchPar
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GraphView& g = p.g;
   unsigned char* base = smem_raw + (size_t)warp * p.smem_per_warp;
+  const size_t stb = stage_bytes(g.d4);  // same per-warp layout as search.cu (the stage is unused here)
   WarpSmem s;
-  s.q4 = reinterpret_cast<float4*>(base);
-  s.wbuf = reinterpret_cast<uint64_t*>(base + (size_t)g.d4 * 16);
-  s.cand_id = reinterpret_cast<uint32_t*>(base + (size_t)g.d4 * 16 + (size_t)p.ef * 8);
+  s.q4 = reinterpret_cast<float4*>(base + stb);
+  s.wbuf = reinterpret_cast<uint64_t*>(base + stb + (size_t)g.d4 * 16);
+  s.cand_id = reinterpret_cast<uint32_t*>(base + stb + (size_t)g.d4 * 16 + (size_t)p.ef * 8);
   s.cand_d = reinterpret_cast<float*>(s.cand_id + 32);
   float* qf = reinterpret_cast<float*>(s.q4);
   const uint32_t slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;

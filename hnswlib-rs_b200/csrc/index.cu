@@ -517,7 +517,7 @@ int Index::search_device(const float* d_queries, size_t nq, size_t k, size_t ef_
   p.filter_bits = d_filter_bits;
   p.stats = stats_on_ ? d_stats_ : nullptr;
   p.status = d_status_;
-  size_t spw = (search_smem_per_warp(p.g.d4, p.ef) + 15) & ~(size_t)15;
+  size_t spw = search_smem_per_warp(p.g.d4, p.ef);
   p.smem_per_warp = (int)spw;
   const int wpb = SEARCH_THREADS / 32;
   const size_t smem = spw * wpb;

@@ -39,7 +39,12 @@ struct SearchParams {
   uint32_t ccap;
 };
 
-inline size_t search_smem_per_warp(int d4, int ef) { return (size_t)d4 * 16 + (size_t)ef * 8 + 32 * 8; }
+// rows of up to 512 bytes are (partly) staged by TMA: STAGE_ROWS rows + an mbarrier per warp
+__host__ __device__ inline size_t stage_bytes(int d4) { return d4 <= 32 ? (size_t)STAGE_ROWS * d4 * 16 : 0; }
+inline size_t search_smem_per_warp(int d4, int ef) {
+  size_t b = stage_bytes(d4) + (size_t)d4 * 16 + (size_t)ef * 8 + 32 * 8 + 16;
+  return (b + 127) & ~(size_t)127;
+}
 
 struct InsertParams {
   GraphView g;
@@ -58,8 +63,8 @@ struct InsertParams {
 };
 
 inline size_t insert_smem_per_warp(int d4, int ef_c, int deg0) {
-  size_t b = (size_t)d4 * 32 + (size_t)ef_c * 8 + 256 + (size_t)deg0 * 12 + (size_t)ef_c * 2;
-  return (b + 15) & ~(size_t)15;
+  size_t b = stage_bytes(d4) + (size_t)d4 * 32 + (size_t)ef_c * 8 + 256 + 16 + (size_t)deg0 * 12 + (size_t)ef_c * 2;
+  return (b + 127) & ~(size_t)127;
 }
 
 cudaError_t launch_insert_search(const InsertParams& p, int metric, int grid, size_t smem, cudaStream_t st,

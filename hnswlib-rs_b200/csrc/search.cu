@@ -13,12 +13,20 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GraphView& g = p.g;
   unsigned char* base = smem_raw + (size_t)warp * p.smem_per_warp;
+  // per-warp layout: [TMA stage][query][queue keys][cand ids][cand dists][mbarrier]
+  const size_t stb = stage_bytes(g.d4);
   WarpSmem s;
-  s.q4 = reinterpret_cast<float4*>(base);
-  s.wbuf = reinterpret_cast<uint64_t*>(base + (size_t)g.d4 * 16);
-  s.cand_id = reinterpret_cast<uint32_t*>(base + (size_t)g.d4 * 16 + (size_t)p.ef * 8);
+  s.q4 = reinterpret_cast<float4*>(base + stb);
+  s.wbuf = reinterpret_cast<uint64_t*>(base + stb + (size_t)g.d4 * 16);
+  s.cand_id = reinterpret_cast<uint32_t*>(base + stb + (size_t)g.d4 * 16 + (size_t)p.ef * 8);
   s.cand_d = reinterpret_cast<float*>(s.cand_id + 32);
   float* qf = reinterpret_cast<float*>(s.q4);
+  Stage stg;
+  stg.buf = stb ? reinterpret_cast<float4*>(base) : nullptr;
+  stg.bar = reinterpret_cast<uint64_t*>(s.cand_d + 32);
+  stg.phase = 0;
+  if (lane == 0) mbar_init(stg.bar, 1);
+  __syncwarp();
 
   const uint32_t slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
   Visited vis;
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
         pivot = new_pivot;  // hnsw.rs:1526-1528
       }
       // ---- layer-0 (lowest populated layer) search, hnsw.rs:1531-1542
-      search_layer<Op, CH, U>(g, s, vis, Q, pivot, p.ef, p.layer0, st, overflow);
+      search_layer<Op, CH, U>(g, s, stg, vis, Q, pivot, p.ef, p.layer0, st, overflow);
       count = min(p.k, min(p.ef, Q.n));  // hnsw.rs:1547
     }
     if (overflow) {

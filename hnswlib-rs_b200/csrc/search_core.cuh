@@ -25,8 +25,8 @@ struct Stats {
 //     so it would trip the stop rule the moment it is popped.
 // Ties on distance are ordered by id (oracle MODE_DET).
 template <class Op, int CH, int U>
-__device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem& s, Visited& vis, SortedQueue& Q,
-                                             uint32_t ep, int ef, int layer, Stats& st, bool& overflow) {
+__device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem& s, Stage& stg, Visited& vis,
+                                             SortedQueue& Q, uint32_t ep, int ef, int layer, Stats& st, bool& overflow) {
   const int lane = lane_id();
   const float4* vec4 = reinterpret_cast<const float4*>(g.vec);
   vis.begin();
@@ -73,7 +73,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
         const int pos = __popc(m & ((1u << lane) - 1u));
         if (fresh) s.cand_id[pos] = nid;
         __syncwarp();
-        warp_dists<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, cnt, s.cand_d);  // hnsw.rs:1026
+        warp_dists_staged<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, cnt, s.cand_d, stg);  // hnsw.rs:1026
         __syncwarp();
         st.evals += cnt;
         const uint64_t key = lane < cnt ? make_key(s.cand_d[lane], s.cand_id[lane]) : ~0ull;

@@ -26,8 +26,9 @@ __device__ __forceinline__ void dists_from_point(const GraphView& g, float4* qe4
   __syncwarp();
 }
 
-template <class Op, int CH, int U>
+template <class Op, int CH, int U, int NS>
 __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertParams p) {
+  using Queue = typename QueueSel<NS>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GraphView& g = p.g;
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
   float4* qe4 = reinterpret_cast<float4*>(base + off);
   off += (size_t)g.d4 * 16;
   s.wbuf = reinterpret_cast<uint64_t*>(base + off);
-  off += (size_t)p.ef_c * 8;
+  off += (size_t)p.q_smem * 8;
   s.cand_id = reinterpret_cast<uint32_t*>(base + off);
   off += 128;
   s.cand_d = reinterpret_cast<float*>(base + off);
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
   const uint32_t slot = blockIdx.x * (BUILD_THREADS / 32) + warp;
   Visited vis;
   vis.init(p.vis, slot);
-  SortedQueue Q;
+  Queue Q;
+  Q.reset(s.wbuf, p.ef_c);
   Stats st{0, 0, 0};
   const float4* vec4 = reinterpret_cast<const float4*>(g.vec);
 
@@ -92,9 +94,9 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
     // be traversed (DESIGN.md "lists above a point's level") and is not materialised.
     for (int l = g.entry_level; l > lv; --l) {
       if (!((mask >> l) & 1u)) continue;  // points_by_layer[l].is_empty() => empty result (942-946)
-      search_layer<Op, CH, U>(g, s, stg, vis, Q, cur, 1, l, st, overflow);
+      search_layer<Op, CH, U, Queue>(g, s, stg, vis, Q, cur, 1, l, st, overflow);
       if (overflow) break;
-      const uint64_t k0 = Q.w[0];
+      const uint64_t k0 = Q.get(0);
       const float t = key_dist(k0);  // == dist(data, ep) recomputed at 1146
       if (t < dist_to_entry) {       // 1147-1150
         cur = key_id(k0);
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
     // ---- layers level..0: ef_construction search + selection (hnsw.rs:1158-1205)
     for (int l = lv; l >= 0 && !overflow; --l) {
       if (!((mask >> l) & 1u)) continue;
-      search_layer<Op, CH, U>(g, s, stg, vis, Q, cur, p.ef_c, l, st, overflow);
+      search_layer<Op, CH, U, Queue>(g, s, stg, vis, Q, cur, p.ef_c, l, st, overflow);
       if (overflow) break;
       const int n = Q.n;
       const int nb = (l == 0) ? g.deg0 : g.M;  // 1177-1183
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
       if (n <= nb && !heuristic_on_few) {
         // 1318-1327: few candidates, take them all nearest first
         for (int i = lane; i < n; i += 32) {
-          const uint64_t k = Q.w[i];
+          const uint64_t k = Q.local(i);
           sel_id[i] = key_id(k);
           sel_d[i] = key_dist(k);
         }
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
       } else {
         int ndisc = 0;
         for (int i = 0; i < n && cnt < nb; ++i) {  // 1365: pop nearest while |out| < nb
-          const uint64_t k = Q.w[i];
+          const uint64_t k = Q.get(i);
           const uint32_t e = key_id(k);
           const float de = key_dist(k);
           bool keep = true;
@@ -159,20 +161,19 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
           // 1399-1409: back-fill with the nearest discarded ones, then the caller sorts (1195).
           // Kept and discarded are both ascending sub-sequences of Q, so a merge by key restores order.
           const int take = min(ndisc, nb - cnt);
-          // serial merge by lane 0 (take <= nb, rare option)
-          if (lane == 0) {
+          // serial merge, executed uniformly by the warp (take <= nb, rare option); lane 0 writes
+          {
             int a = cnt - 1, b = take - 1, o = cnt + take - 1;
             while (b >= 0) {
-              const uint64_t kb = Q.w[disc[b]] & ~1ull;
-              if (a >= 0 && make_key(sel_d[a], sel_id[a]) > kb) {
-                sel_id[o] = sel_id[a];
-                sel_d[o] = sel_d[a];
-                --a;
-              } else {
-                sel_id[o] = key_id(kb);
-                sel_d[o] = key_dist(kb);
-                --b;
+              const uint64_t kb = Q.get(disc[b]) & ~1ull;
+              const bool from_a = a >= 0 && make_key(sel_d[a], sel_id[a]) > kb;
+              __syncwarp();
+              if (lane == 0) {
+                sel_id[o] = from_a ? sel_id[a] : key_id(kb);
+                sel_d[o] = from_a ? sel_d[a] : key_dist(kb);
               }
+              __syncwarp();
+              if (from_a) --a; else --b;
               --o;
             }
           }
@@ -331,13 +332,13 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_link_kernel(InsertParams
   (void)lane;
 }
 
-template <class Op>
+template <class Op, int NS>
 static cudaError_t launch_insert_for_op(const InsertParams& p, int grid, size_t smem, cudaStream_t st, bool query_only,
                                         int* blocks_per_sm) {
   const int ch = p.g.d4 / 8;
 #define HB_LAUNCH(CHV, UV)                                                                              \
   do {                                                                                                  \
-    auto kern = insert_search_kernel<Op, CHV, UV>;                                                      \
+    auto kern = insert_search_kernel<Op, CHV, UV, NS>;                                                  \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                     \
     if (blocks_per_sm) {                                                                                \
@@ -354,16 +355,23 @@ static cudaError_t launch_insert_for_op(const InsertParams& p, int grid, size_t 
 #undef HB_LAUNCH
 }
 
+template <class Op>
+static cudaError_t launch_insert_common(const InsertParams& p, int grid, size_t smem, cudaStream_t st, bool query_only,
+                                        int* blocks_per_sm) {
+  if (p.q_smem == 0) return launch_insert_for_op<Op, 8>(p, grid, smem, st, query_only, blocks_per_sm);
+  return launch_insert_for_op<Op, 0>(p, grid, smem, st, query_only, blocks_per_sm);
+}
+
 cudaError_t launch_insert_search(const InsertParams& p, int metric, int grid, size_t smem, cudaStream_t st,
                                  bool query_only, int* blocks_per_sm) {
   switch (metric) {
-    case METRIC_L1: return launch_insert_for_op<OpL1>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_L2: return launch_insert_for_op<OpL2>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_DOT: return launch_insert_for_op<OpDot>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_COSINE: return launch_insert_for_op<OpCosine>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_HELLINGER: return launch_insert_for_op<OpHellinger>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_JEFFREYS: return launch_insert_for_op<OpJeffreys>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_JENSENSHANNON: return launch_insert_for_op<OpJS>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_L1: return launch_insert_common<OpL1>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_L2: return launch_insert_common<OpL2>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_DOT: return launch_insert_common<OpDot>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_COSINE: return launch_insert_common<OpCosine>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_HELLINGER: return launch_insert_for_op<OpHellinger, 0>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_JEFFREYS: return launch_insert_for_op<OpJeffreys, 0>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_JENSENSHANNON: return launch_insert_for_op<OpJS, 0>(p, grid, smem, st, query_only, blocks_per_sm);
   }
   return cudaErrorInvalidValue;
 }

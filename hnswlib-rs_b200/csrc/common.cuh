@@ -436,6 +436,19 @@ struct SortedQueue {
     n = 0;
     cap = ef;
   }
+  __device__ __forceinline__ uint64_t get(int i) const { return w[i]; }
+  __device__ __forceinline__ uint64_t local(int i) const { return w[i]; }  // i == lane (mod 32)
+  __device__ __forceinline__ void mark_expanded(int i) {
+    __syncwarp();
+    if (lane_id() == 0) w[i] |= 1ull;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void push_first(uint64_t key) {
+    if (lane_id() == 0) w[0] = key;
+    n = 1;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void clear() { n = 0; }
   // index of the nearest unexpanded entry, or -1
   __device__ __forceinline__ int first_unexpanded() const {
     const int lane = lane_id();
@@ -486,6 +499,91 @@ struct SortedQueue {
     __syncwarp();
     n = new_n;
   }
+};
+
+// Same queue held in registers: entry i lives in lane (i & 31), stripe (i >> 5); unused slots hold ~0 (whose
+// low bit reads as "expanded", so scans skip them).  Sorted insert = ballot rank + one shuffle-up per stripe.
+// No shared-memory traffic and no __syncwarp on the hot path.  Capacity 32*NS >= ef.
+template <int NS>
+struct RegQueue {
+  uint64_t w[NS];
+  int n;
+  int cap;
+  uint64_t fkey;  // largest key (flag cleared) when full, else ~0; warp-uniform
+
+  __device__ __forceinline__ void reset(uint64_t*, int ef) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) w[s] = ~0ull;
+    n = 0;
+    cap = ef;
+    fkey = ~0ull;
+  }
+  __device__ __forceinline__ void clear() { reset(nullptr, cap); }
+  __device__ __forceinline__ uint64_t get(int i) const {
+    uint64_t v = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if ((i >> 5) == s) v = w[s];
+    return __shfl_sync(FULL, v, i & 31);
+  }
+  __device__ __forceinline__ uint64_t local(int i) const {  // entry i for the lane with lane == (i & 31)
+    uint64_t v = ~0ull;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if ((i >> 5) == s) v = w[s];
+    return v;
+  }
+  __device__ __forceinline__ void mark_expanded(int i) {
+    const bool mine = lane_id() == (i & 31);
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (mine && (i >> 5) == s) w[s] |= 1ull;
+  }
+  __device__ __forceinline__ void push_first(uint64_t key) {
+    reset(nullptr, cap);
+    if (lane_id() == 0) w[0] = key;
+    n = 1;
+    fkey = cap == 1 ? key : ~0ull;
+  }
+  __device__ __forceinline__ int first_unexpanded() const { return next_unexpanded(0); }
+  __device__ __forceinline__ int next_unexpanded(int from) const {
+    const int lane = lane_id();
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const unsigned m = __ballot_sync(FULL, ((w[s] & 1ull) == 0ull) && (32 * s + lane >= from));
+      if (m) return 32 * s + __ffs(m) - 1;
+    }
+    return -1;
+  }
+  __device__ __forceinline__ bool accepts(uint64_t key) const { return n < cap || key < fkey; }
+  __device__ __forceinline__ void insert(uint64_t key) {
+    const int lane = lane_id();
+    int pos = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) pos += __popc(__ballot_sync(FULL, w[s] < key));
+#pragma unroll
+    for (int s = NS - 1; s >= 0; --s) {
+      const uint64_t up = __shfl_up_sync(FULL, w[s], 1);
+      uint64_t carry = 0;
+      if (s > 0) carry = __shfl_sync(FULL, w[s - 1], 31);
+      const int i = 32 * s + lane;
+      const uint64_t moved = lane == 0 ? carry : up;
+      uint64_t nv = i > pos ? moved : (i == pos ? key : w[s]);
+      if (i >= cap) nv = ~0ull;
+      w[s] = nv;
+    }
+    n = n < cap ? n + 1 : cap;
+    fkey = n == cap ? (get(cap - 1) & ~1ull) : ~0ull;
+  }
+};
+
+template <int NS>
+struct QueueSel {
+  typedef RegQueue<NS> type;
+};
+template <>
+struct QueueSel<0> {
+  typedef SortedQueue type;
 };
 
 }  // namespace hb

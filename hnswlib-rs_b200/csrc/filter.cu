@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_filter_kernel(SearchPar
   WarpSmem s;
   s.q4 = reinterpret_cast<float4*>(base + stb);
   s.wbuf = reinterpret_cast<uint64_t*>(base + stb + (size_t)g.d4 * 16);
-  s.cand_id = reinterpret_cast<uint32_t*>(base + stb + (size_t)g.d4 * 16 + (size_t)p.ef * 8);
+  s.cand_id = reinterpret_cast<uint32_t*>(base + stb + (size_t)g.d4 * 16 + (size_t)p.q_smem * 8);
   s.cand_d = reinterpret_cast<float*>(s.cand_id + 32);
   float* qf = reinterpret_cast<float*>(s.q4);
   const uint32_t slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;

@@ -252,7 +252,9 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
   p.locks = d_locks_.p;
   p.stats = nullptr;
   p.status = d_status_;
-  const size_t spw = insert_smem_per_warp(p.g.d4, ef_c, p.g.deg0);
+  // the insert kernel keeps its queue in registers (8 stripes) when ef_construction <= 256
+  p.q_smem = (queue_stripes(ef_c, metric) != 0 && ef_c <= 256) ? 0 : ef_c;
+  const size_t spw = insert_smem_per_warp(p.g.d4, ef_c, p.g.deg0, p.q_smem);
   p.smem_per_warp = (int)spw;
   const size_t smem = spw * (BUILD_THREADS / 32);
   if (smem > 220 * 1024) return fail("ef_construction / dimension too large for the insert kernel's shared memory");
@@ -517,12 +519,13 @@ int Index::search_device(const float* d_queries, size_t nq, size_t k, size_t ef_
   p.filter_bits = d_filter_bits;
   p.stats = stats_on_ ? d_stats_ : nullptr;
   p.status = d_status_;
-  size_t spw = search_smem_per_warp(p.g.d4, p.ef);
+  const bool filtered = d_filter_bits != nullptr;
+  p.q_smem = (!filtered && queue_stripes(p.ef, metric) != 0) ? 0 : p.ef;
+  size_t spw = search_smem_per_warp(p.g.d4, p.q_smem);
   p.smem_per_warp = (int)spw;
   const int wpb = SEARCH_THREADS / 32;
   const size_t smem = spw * wpb;
   if (smem > 220 * 1024) return fail("ef / dimension too large for the search kernel's shared memory");
-  const bool filtered = d_filter_bits != nullptr;
   p.cbuf = nullptr;
   p.ccap = 0;
   int bps = 0;

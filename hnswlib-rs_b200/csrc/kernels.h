@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -35,14 +36,27 @@ struct SearchParams {
   unsigned long long* stats;    // nullptr or [3]: evals, expansions, adjacency ids read
   int* status;                  // set to 1 on visited-table overflow
   int smem_per_warp;
+  int q_smem;  // queue slots kept in shared memory (0 when the queue lives in registers)
   uint64_t* cbuf;  // filtered search only: candidate queue C, [slots][ccap] keys
   uint32_t ccap;
 };
 
 // rows of up to 512 bytes are (partly) staged by TMA: STAGE_ROWS rows + an mbarrier per warp
 __host__ __device__ inline size_t stage_bytes(int d4) { return d4 <= 32 ? (size_t)STAGE_ROWS * d4 * 16 : 0; }
-inline size_t search_smem_per_warp(int d4, int ef) {
-  size_t b = stage_bytes(d4) + (size_t)d4 * 16 + (size_t)ef * 8 + 32 * 8 + 16;
+// register-queue stripes for a given ef (0 = queue in shared memory)
+// Measured on B200 (profiles/README.md): at 64 registers/thread the register queue spills and is ~5 % slower than
+// the shared-memory queue, so it is opt-in (HNSW_B200_REGQUEUE=1) until the kernel's register budget changes.
+inline int queue_stripes(int ef, int metric) {
+  static const bool enabled = [] { const char* e = getenv("HNSW_B200_REGQUEUE"); return e && e[0] == '1'; }();
+  if (!enabled) return 0;
+  const bool common = metric == METRIC_L1 || metric == METRIC_L2 || metric == METRIC_DOT || metric == METRIC_COSINE;
+  if (!common) return 0;
+  if (ef <= 64) return 2;
+  if (ef <= 256) return 8;
+  return 0;
+}
+inline size_t search_smem_per_warp(int d4, int q_smem) {
+  size_t b = stage_bytes(d4) + (size_t)d4 * 16 + (size_t)q_smem * 8 + 32 * 8 + 16;
   return (b + 127) & ~(size_t)127;
 }
 
@@ -60,10 +74,11 @@ struct InsertParams {
   unsigned long long* stats;
   int* status;
   int smem_per_warp;
+  int q_smem;
 };
 
-inline size_t insert_smem_per_warp(int d4, int ef_c, int deg0) {
-  size_t b = stage_bytes(d4) + (size_t)d4 * 32 + (size_t)ef_c * 8 + 256 + 16 + (size_t)deg0 * 12 + (size_t)ef_c * 2;
+inline size_t insert_smem_per_warp(int d4, int ef_c, int deg0, int q_smem) {
+  size_t b = stage_bytes(d4) + (size_t)d4 * 32 + (size_t)q_smem * 8 + 256 + 16 + (size_t)deg0 * 12 + (size_t)ef_c * 2;
   return (b + 127) & ~(size_t)127;
 }
 

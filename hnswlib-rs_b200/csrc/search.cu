@@ -7,8 +7,9 @@
 
 namespace hb {
 
-template <class Op, int CH, int U>
+template <class Op, int CH, int U, int NS>
 __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams p) {
+  using Queue = typename QueueSel<NS>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GraphView& g = p.g;
@@ -18,7 +19,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
   WarpSmem s;
   s.q4 = reinterpret_cast<float4*>(base + stb);
   s.wbuf = reinterpret_cast<uint64_t*>(base + stb + (size_t)g.d4 * 16);
-  s.cand_id = reinterpret_cast<uint32_t*>(base + stb + (size_t)g.d4 * 16 + (size_t)p.ef * 8);
+  s.cand_id = reinterpret_cast<uint32_t*>(base + stb + (size_t)g.d4 * 16 + (size_t)p.q_smem * 8);
   s.cand_d = reinterpret_cast<float*>(s.cand_id + 32);
   float* qf = reinterpret_cast<float*>(s.q4);
   Stage stg;
@@ -31,7 +32,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
   const uint32_t slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
   Visited vis;
   vis.init(p.vis, slot);
-  SortedQueue Q;
+  Queue Q;
+  Q.reset(s.wbuf, p.ef);
   Stats st{0, 0, 0};
   const float4* vec4 = reinterpret_cast<const float4*>(g.vec);
 
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
         pivot = new_pivot;  // hnsw.rs:1526-1528
       }
       // ---- layer-0 (lowest populated layer) search, hnsw.rs:1531-1542
-      search_layer<Op, CH, U>(g, s, stg, vis, Q, pivot, p.ef, p.layer0, st, overflow);
+      search_layer<Op, CH, U, Queue>(g, s, stg, vis, Q, pivot, p.ef, p.layer0, st, overflow);
       count = min(p.k, min(p.ef, Q.n));  // hnsw.rs:1547
     }
     if (overflow) {
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
     const size_t ob = (size_t)qi * p.k;
     for (int j = lane; j < p.k; j += 32) {
       if (j < count) {
-        const uint64_t key = Q.w[j];
+        const uint64_t key = Q.local(j);
         const uint32_t id = key_id(key);
         p.out_nb[ob + j] = NeighbourOut{g.origin[id], key_dist(key), id};
       } else {
@@ -121,13 +123,13 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
   }
 }
 
-template <class Op>
+template <class Op, int NS>
 static cudaError_t launch_for_op(const SearchParams& p, int grid, size_t smem, cudaStream_t st, bool query_only,
                                  int* blocks_per_sm) {
   const int ch = p.g.d4 / 8;
 #define HB_LAUNCH(CHV, UV)                                                                                      \
   do {                                                                                                          \
-    auto kern = search_kernel<Op, CHV, UV>;                                                                     \
+    auto kern = search_kernel<Op, CHV, UV, NS>;                                                                 \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
     if (e != cudaSuccess) return e;                                                                             \
     if (blocks_per_sm) {                                                                                        \
@@ -144,16 +146,25 @@ static cudaError_t launch_for_op(const SearchParams& p, int grid, size_t smem, c
 #undef HB_LAUNCH
 }
 
+template <class Op>
+static cudaError_t launch_common(const SearchParams& p, int grid, size_t smem, cudaStream_t st, bool query_only,
+                                 int* blocks_per_sm) {
+  const int ns = p.q_smem ? 0 : queue_stripes(p.ef, METRIC_L2);
+  if (ns == 2) return launch_for_op<Op, 2>(p, grid, smem, st, query_only, blocks_per_sm);
+  if (ns == 8) return launch_for_op<Op, 8>(p, grid, smem, st, query_only, blocks_per_sm);
+  return launch_for_op<Op, 0>(p, grid, smem, st, query_only, blocks_per_sm);
+}
+
 cudaError_t launch_search(const SearchParams& p, int metric, int grid, size_t smem, cudaStream_t st, bool query_only,
                           int* blocks_per_sm) {
   switch (metric) {
-    case METRIC_L1: return launch_for_op<OpL1>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_L2: return launch_for_op<OpL2>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_DOT: return launch_for_op<OpDot>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_COSINE: return launch_for_op<OpCosine>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_HELLINGER: return launch_for_op<OpHellinger>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_JEFFREYS: return launch_for_op<OpJeffreys>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_JENSENSHANNON: return launch_for_op<OpJS>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_L1: return launch_common<OpL1>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_L2: return launch_common<OpL2>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_DOT: return launch_common<OpDot>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_COSINE: return launch_common<OpCosine>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_HELLINGER: return launch_for_op<OpHellinger, 0>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_JEFFREYS: return launch_for_op<OpJeffreys, 0>(p, grid, smem, st, query_only, blocks_per_sm);
+    case METRIC_JENSENSHANNON: return launch_for_op<OpJS, 0>(p, grid, smem, st, query_only, blocks_per_sm);
   }
   return cudaErrorInvalidValue;
 }

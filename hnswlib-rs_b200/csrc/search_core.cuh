@@ -24,9 +24,9 @@ struct Stats {
 //     a candidate evicted from W has key > every key of the (full) W, and f only decreases afterwards,
 //     so it would trip the stop rule the moment it is popped.
 // Ties on distance are ordered by id (oracle MODE_DET).
-template <class Op, int CH, int U>
+template <class Op, int CH, int U, class Queue>
 __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem& s, Stage& stg, Visited& vis,
-                                             SortedQueue& Q, uint32_t ep, int ef, int layer, Stats& st, bool& overflow) {
+                                             Queue& Q, uint32_t ep, int ef, int layer, Stats& st, bool& overflow) {
   const int lane = lane_id();
   const float4* vec4 = reinterpret_cast<const float4*>(g.vec);
   vis.begin();
@@ -38,27 +38,24 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
   const float d0 = s.cand_d[0];
   vis.test_and_set(ep, lane == 0);  // hnsw.rs:955-956
   Q.reset(s.wbuf, ef);
-  if (lane == 0) s.wbuf[0] = make_key(d0, ep);  // hnsw.rs:958-967 (ep enters W and C)
-  Q.n = 1;
-  __syncwarp();
+  Q.push_first(make_key(d0, ep));  // hnsw.rs:958-967 (ep enters W and C)
   for (;;) {
     const int idx = Q.first_unexpanded();  // C.pop(): nearest candidate (hnsw.rs:971)
     if (idx < 0) break;                    // C empty (969) or stop rule (981-993), see header
-    const uint64_t ck = Q.w[idx];
-    const uint32_t c = key_id(ck);
-    __syncwarp();
-    if (lane == 0) Q.w[idx] = ck | 1ull;
-    __syncwarp();
+    const uint32_t c = key_id(Q.get(idx));
+    Q.mark_expanded(idx);
     int cap;
     const uint32_t* ids = list_ids(g, c, layer, cap);  // hnsw.rs:1006
     st.expansions += 1;
     {  // pull the adjacency rows of the two most likely next candidates towards L2 while this one is expanded
-      const int i1 = Q.next_unexpanded(0);
+      const int i1 = Q.next_unexpanded(idx + 1);  // entries before idx are expanded (idx was the first open one)
       const int i2 = i1 >= 0 ? Q.next_unexpanded(i1 + 1) : -1;
-      const int pick = lane == 0 ? i1 : (lane == 1 ? i2 : -1);
-      if (pick >= 0) {
+      const uint32_t c1 = i1 >= 0 ? key_id(Q.get(i1)) : INVALID_ID;
+      const uint32_t c2 = i2 >= 0 ? key_id(Q.get(i2)) : INVALID_ID;
+      const uint32_t pc = lane == 0 ? c1 : (lane == 1 ? c2 : INVALID_ID);
+      if (pc != INVALID_ID) {
         int pcap;
-        const uint32_t* pids = list_ids(g, key_id(Q.w[pick]), layer, pcap);
+        const uint32_t* pids = list_ids(g, pc, layer, pcap);
         if (pids) asm volatile("prefetch.global.L2 [%0];" ::"l"(pids));
       }
     }

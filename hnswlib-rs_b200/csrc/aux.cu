@@ -10,8 +10,8 @@ namespace hb {
 
 struct AuxParams {
   GraphView g;
-  const float* queries;
-  int d;
+  const void* queries;  // [nq][q_bytes] raw element bytes
+  int q_bytes;
   uint32_t nq;
   const uint32_t* cand;  // [nq][m]
   uint32_t m;
@@ -27,21 +27,19 @@ __global__ void __launch_bounds__(256) dist_batch_kernel(AuxParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* base = smem_raw + (size_t)warp * p.smem_per_warp;
-  float4* q4 = reinterpret_cast<float4*>(base);
+  uint4* q4 = reinterpret_cast<uint4*>(base);
   uint32_t* cid = reinterpret_cast<uint32_t*>(base + (size_t)p.g.d4 * 16);
   float* cd = reinterpret_cast<float*>(cid + 32);
-  float* qf = reinterpret_cast<float*>(q4);
-  const float4* vec4 = reinterpret_cast<const float4*>(p.g.vec);
+  const uint4* vec4 = reinterpret_cast<const uint4*>(p.g.vec);
   const uint32_t wstride = gridDim.x * 8;
   for (uint32_t qi = blockIdx.x * 8 + warp; qi < p.nq; qi += wstride) {
     __syncwarp();
-    for (int i = lane; i < p.g.d4 * 4; i += 32) qf[i] = i < p.d ? p.queries[(size_t)qi * p.d + i] : 0.f;
-    __syncwarp();
+    stage_row_bytes(q4, reinterpret_cast<const char*>(p.queries) + (size_t)qi * p.q_bytes, p.q_bytes, p.g.d4 * 16);
     for (uint32_t b = 0; b < p.m; b += 32) {
       const int cnt = min(32u, p.m - b);
       if (lane < cnt) cid[lane] = p.cand[(size_t)qi * p.m + b + lane];
       __syncwarp();
-      warp_dists<Op, CH, U>(vec4, p.g.d4, q4, cid, cnt, cd);
+      warp_dists<Op, CH, U>(vec4, p.g.d4, p.g.dim, q4, cid, cnt, cd);
       __syncwarp();
       if (lane < cnt) p.out[(size_t)qi * p.m + b + lane] = cd[lane];
       __syncwarp();
@@ -54,24 +52,22 @@ __global__ void __launch_bounds__(256) bruteforce_kernel(AuxParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* base = smem_raw + (size_t)warp * p.smem_per_warp;
-  float4* q4 = reinterpret_cast<float4*>(base);
+  uint4* q4 = reinterpret_cast<uint4*>(base);
   uint32_t* cid = reinterpret_cast<uint32_t*>(base + (size_t)p.g.d4 * 16);
   float* cd = reinterpret_cast<float*>(cid + 32);
   uint64_t* wbuf = reinterpret_cast<uint64_t*>(cd + 32);
-  float* qf = reinterpret_cast<float*>(q4);
-  const float4* vec4 = reinterpret_cast<const float4*>(p.g.vec);
+  const uint4* vec4 = reinterpret_cast<const uint4*>(p.g.vec);
   const uint32_t wstride = gridDim.x * 8;
   SortedQueue Q;
   for (uint32_t qi = blockIdx.x * 8 + warp; qi < p.nq; qi += wstride) {
     __syncwarp();
-    for (int i = lane; i < p.g.d4 * 4; i += 32) qf[i] = i < p.d ? p.queries[(size_t)qi * p.d + i] : 0.f;
+    stage_row_bytes(q4, reinterpret_cast<const char*>(p.queries) + (size_t)qi * p.q_bytes, p.q_bytes, p.g.d4 * 16);
     Q.reset(wbuf, p.k);
-    __syncwarp();
     for (uint32_t b = 0; b < p.g.n; b += 32) {
       const int cnt = min(32u, p.g.n - b);
       cid[lane] = b + lane;
       __syncwarp();
-      warp_dists<Op, CH, U>(vec4, p.g.d4, q4, cid, cnt, cd);
+      warp_dists<Op, CH, U>(vec4, p.g.d4, p.g.dim, q4, cid, cnt, cd);
       __syncwarp();
       const uint64_t key = lane < cnt ? make_key(cd[lane], b + lane) : ~0ull;
       unsigned acc = __ballot_sync(FULL, lane < cnt && Q.accepts(key));
@@ -108,24 +104,19 @@ static cudaError_t launch_aux_for_op(const AuxParams& p, bool brute, int grid, s
     }                                                                                                     \
     return cudaGetLastError();                                                                            \
   } while (0)
-  if (ch == 1) HB_LAUNCH(1, 4);
-  if (ch == 2) HB_LAUNCH(2, 4);
-  if (ch == 4) HB_LAUNCH(4, 2);
+  if constexpr (Specialise<Op>::value) {
+    if (ch == 1) HB_LAUNCH(1, 4);
+    if (ch == 4) HB_LAUNCH(4, 2);
+  }
   HB_LAUNCH(0, 2);
 #undef HB_LAUNCH
 }
 
-static cudaError_t launch_aux(const AuxParams& p, int metric, bool brute, int grid, size_t smem, cudaStream_t st) {
-  switch (metric) {
-    case METRIC_L1: return launch_aux_for_op<OpL1>(p, brute, grid, smem, st);
-    case METRIC_L2: return launch_aux_for_op<OpL2>(p, brute, grid, smem, st);
-    case METRIC_DOT: return launch_aux_for_op<OpDot>(p, brute, grid, smem, st);
-    case METRIC_COSINE: return launch_aux_for_op<OpCosine>(p, brute, grid, smem, st);
-    case METRIC_HELLINGER: return launch_aux_for_op<OpHellinger>(p, brute, grid, smem, st);
-    case METRIC_JEFFREYS: return launch_aux_for_op<OpJeffreys>(p, brute, grid, smem, st);
-    case METRIC_JENSENSHANNON: return launch_aux_for_op<OpJS>(p, brute, grid, smem, st);
-  }
-  return cudaErrorInvalidValue;
+static cudaError_t launch_aux(const AuxParams& p, int metric, int dtype, bool brute, int grid, size_t smem, cudaStream_t st) {
+  return dispatch_op(metric, dtype, [&](auto tag) -> cudaError_t {
+    using Op = typename decltype(tag)::type;
+    return launch_aux_for_op<Op>(p, brute, grid, smem, st);
+  });
 }
 
 #define HB_CUDA(call)                                     \
@@ -134,24 +125,24 @@ static cudaError_t launch_aux(const AuxParams& p, int metric, bool brute, int gr
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
-int Index::dist_batch(const float* queries, size_t nq, int d, const uint32_t* cand, size_t m, float* out) {
+int Index::dist_batch(const void* queries, size_t nq, int d, const uint32_t* cand, size_t m, float* out) {
   if (nq == 0 || m == 0) return 0;
   if (d != dim) return fail("query length differs from the index dimension");
   for (size_t i = 0; i < nq * m; ++i)
     if (cand[i] >= n) return fail("candidate id out of range");
   HB_CUDA(cudaSetDevice(device));
-  float* dq = nullptr;
+  void* dq = nullptr;
   uint32_t* dc = nullptr;
   float* dout = nullptr;
-  HB_CUDA(cudaMalloc(&dq, nq * d * 4));
+  HB_CUDA(cudaMalloc(&dq, nq * d * es));
   HB_CUDA(cudaMalloc(&dc, nq * m * 4));
   HB_CUDA(cudaMalloc(&dout, nq * m * 4));
-  cudaMemcpyAsync(dq, queries, nq * d * 4, cudaMemcpyHostToDevice, stream_);
+  cudaMemcpyAsync(dq, queries, nq * d * es, cudaMemcpyHostToDevice, stream_);
   cudaMemcpyAsync(dc, cand, nq * m * 4, cudaMemcpyHostToDevice, stream_);
   AuxParams p{};
   p.g = view();
   p.queries = dq;
-  p.d = d;
+  p.q_bytes = d * es;
   p.nq = (uint32_t)nq;
   p.cand = dc;
   p.m = (uint32_t)m;
@@ -159,7 +150,7 @@ int Index::dist_batch(const float* queries, size_t nq, int d, const uint32_t* ca
   p.smem_per_warp = p.g.d4 * 16 + 256;
   const size_t smem = (size_t)p.smem_per_warp * 8;
   const int grid = (int)std::min<size_t>((size_t)sm_count_ * 8, (nq + 7) / 8);
-  cudaError_t e = launch_aux(p, metric, false, grid, smem, stream_);
+  cudaError_t e = launch_aux(p, metric, dtype, false, grid, smem, stream_);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, nq * m * 4, cudaMemcpyDeviceToHost, stream_);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
   cudaFree(dq);
@@ -169,21 +160,21 @@ int Index::dist_batch(const float* queries, size_t nq, int d, const uint32_t* ca
   return 0;
 }
 
-int Index::bruteforce(const float* queries, size_t nq, int d, size_t k, uint32_t* out_ids, float* out_dist) {
+int Index::bruteforce(const void* queries, size_t nq, int d, size_t k, uint32_t* out_ids, float* out_dist) {
   if (nq == 0 || k == 0) return 0;
   if (d != dim) return fail("query length differs from the index dimension");
   HB_CUDA(cudaSetDevice(device));
-  float* dq = nullptr;
+  void* dq = nullptr;
   uint32_t* dids = nullptr;
   float* dd = nullptr;
-  HB_CUDA(cudaMalloc(&dq, nq * d * 4));
+  HB_CUDA(cudaMalloc(&dq, nq * d * es));
   HB_CUDA(cudaMalloc(&dids, nq * k * 4));
   HB_CUDA(cudaMalloc(&dd, nq * k * 4));
-  cudaMemcpyAsync(dq, queries, nq * d * 4, cudaMemcpyHostToDevice, stream_);
+  cudaMemcpyAsync(dq, queries, nq * d * es, cudaMemcpyHostToDevice, stream_);
   AuxParams p{};
   p.g = view();
   p.queries = dq;
-  p.d = d;
+  p.q_bytes = d * es;
   p.nq = (uint32_t)nq;
   p.k = (int)k;
   p.out_ids = dids;
@@ -195,7 +186,7 @@ int Index::bruteforce(const float* queries, size_t nq, int d, size_t k, uint32_t
     return fail("k / dimension too large for the brute-force kernel");
   }
   const int grid = (int)std::min<size_t>((size_t)sm_count_ * 4, (nq + 7) / 8);
-  cudaError_t e = launch_aux(p, metric, true, grid, smem, stream_);
+  cudaError_t e = launch_aux(p, metric, dtype, true, grid, smem, stream_);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_ids, dids, nq * k * 4, cudaMemcpyDeviceToHost, stream_);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist, dd, nq * k * 4, cudaMemcpyDeviceToHost, stream_);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);

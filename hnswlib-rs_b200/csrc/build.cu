@@ -15,14 +15,14 @@ namespace hb {
 
 // dists from the vector of point `e` to kept[0..cnt): stage e's row as the "query"
 template <class Op, int CH, int U>
-__device__ __forceinline__ void dists_from_point(const GraphView& g, float4* qe4, uint32_t e, const uint32_t* kept,
+__device__ __forceinline__ void dists_from_point(const GraphView& g, uint4* qe4, uint32_t e, const uint32_t* kept,
                                                  int cnt, float* out) {
-  const float4* vec4 = reinterpret_cast<const float4*>(g.vec);
+  const uint4* vec4 = reinterpret_cast<const uint4*>(g.vec);
   const int lane = lane_id();
   __syncwarp();
   for (int i = lane; i < g.d4; i += 32) qe4[i] = __ldg(vec4 + (size_t)e * g.d4 + i);
   __syncwarp();
-  warp_dists<Op, CH, U>(vec4, g.d4, qe4, kept, cnt, out);
+  warp_dists<Op, CH, U>(vec4, g.d4, g.dim, qe4, kept, cnt, out);
   __syncwarp();
 }
 
@@ -37,10 +37,10 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
   WarpSmem s;
   size_t off = stage_bytes(g.d4);
   Stage stg;
-  stg.buf = off ? reinterpret_cast<float4*>(base) : nullptr;
-  s.q4 = reinterpret_cast<float4*>(base + off);
+  stg.buf = off ? reinterpret_cast<uint4*>(base) : nullptr;
+  s.q4 = reinterpret_cast<uint4*>(base + off);
   off += (size_t)g.d4 * 16;
-  float4* qe4 = reinterpret_cast<float4*>(base + off);
+  uint4* qe4 = reinterpret_cast<uint4*>(base + off);
   off += (size_t)g.d4 * 16;
   s.wbuf = reinterpret_cast<uint64_t*>(base + off);
   off += (size_t)p.q_smem * 8;
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
   Queue Q;
   Q.reset(s.wbuf, p.ef_c);
   Stats st{0, 0, 0};
-  const float4* vec4 = reinterpret_cast<const float4*>(g.vec);
+  const uint4* vec4 = reinterpret_cast<const uint4*>(g.vec);
 
   for (;;) {
     uint32_t wi = 0;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
     // dist_to_entry, hnsw.rs:1110-1112
     if (lane == 0) s.cand_id[0] = cur;
     __syncwarp();
-    warp_dists<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, 1, s.cand_d);
+    warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, 1, s.cand_d);
     __syncwarp();
     float dist_to_entry = s.cand_d[0];
     // ---- layers above the new point's level: ef = 1 (hnsw.rs:1114-1155).  The reference also pushes
@@ -348,32 +348,24 @@ static cudaError_t launch_insert_for_op(const InsertParams& p, int grid, size_t 
     if (!query_only) kern<<<grid, BUILD_THREADS, smem, st>>>(p);                                        \
     return cudaGetLastError();                                                                          \
   } while (0)
-  if (ch == 1) HB_LAUNCH(1, 4);
-  if (ch == 2) HB_LAUNCH(2, 4);
-  if (ch == 4) HB_LAUNCH(4, 2);
+  if constexpr (Specialise<Op>::value) {
+    if (ch == 1) HB_LAUNCH(1, 4);
+    if (ch == 2) HB_LAUNCH(2, 4);
+    if (ch == 4) HB_LAUNCH(4, 2);
+  }
   HB_LAUNCH(0, 2);
 #undef HB_LAUNCH
 }
 
-template <class Op>
-static cudaError_t launch_insert_common(const InsertParams& p, int grid, size_t smem, cudaStream_t st, bool query_only,
-                                        int* blocks_per_sm) {
-  if (p.q_smem == 0) return launch_insert_for_op<Op, 8>(p, grid, smem, st, query_only, blocks_per_sm);
-  return launch_insert_for_op<Op, 0>(p, grid, smem, st, query_only, blocks_per_sm);
-}
-
-cudaError_t launch_insert_search(const InsertParams& p, int metric, int grid, size_t smem, cudaStream_t st,
+cudaError_t launch_insert_search(const InsertParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
                                  bool query_only, int* blocks_per_sm) {
-  switch (metric) {
-    case METRIC_L1: return launch_insert_common<OpL1>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_L2: return launch_insert_common<OpL2>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_DOT: return launch_insert_common<OpDot>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_COSINE: return launch_insert_common<OpCosine>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_HELLINGER: return launch_insert_for_op<OpHellinger, 0>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_JEFFREYS: return launch_insert_for_op<OpJeffreys, 0>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_JENSENSHANNON: return launch_insert_for_op<OpJS, 0>(p, grid, smem, st, query_only, blocks_per_sm);
-  }
-  return cudaErrorInvalidValue;
+  return dispatch_op(metric, dtype, [&](auto tag) -> cudaError_t {
+    using Op = typename decltype(tag)::type;
+    if constexpr (Specialise<Op>::value) {
+      if (p.q_smem == 0) return launch_insert_for_op<Op, 8>(p, grid, smem, st, query_only, blocks_per_sm);
+    }
+    return launch_insert_for_op<Op, 0>(p, grid, smem, st, query_only, blocks_per_sm);
+  });
 }
 
 cudaError_t launch_insert_link(const InsertParams& p, int grid, cudaStream_t st) {

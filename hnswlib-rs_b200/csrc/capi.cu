@@ -12,9 +12,13 @@
 using hb::Index;
 using hb::NeighbourOut;
 
-struct HnswApif32 {
-  Index* ix;
-};
+// every typed handle of libext.rs (HnswApif32, HnswApii32, HnswApiu32, HnswApiu16, HnswApiu8) has this layout
+struct HnswApif32 { Index* ix; };
+struct HnswApii32 { Index* ix; };
+struct HnswApiu32 { Index* ix; };
+struct HnswApiu16 { Index* ix; };
+struct HnswApiu8 { Index* ix; };
+struct AnyApi { Index* ix; };
 
 static thread_local std::string g_err;
 static int g_device = 0;
@@ -41,18 +45,20 @@ static int metric_from_name(const uint8_t* name, size_t len) {
   if (s == "DistHellinger") return hb::METRIC_HELLINGER;
   if (s == "DistJeffreys") return hb::METRIC_JEFFREYS;
   if (s == "DistJensenShannon") return hb::METRIC_JENSENSHANNON;
+  if (s == "DistHamming") return hb::METRIC_HAMMING;
+  if (s == "DistJaccard") return hb::METRIC_JACCARD;
   return -1;
 }
 
-static const HnswApif32* make_index(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname,
-                                    size_t max_elements, size_t max_layer) {
+static void* make_index(int dtype, size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname,
+                        size_t max_elements, size_t max_layer) {
   if (!cdistname) {
     set_err("distance name is NULL");
     return nullptr;
   }
   const int metric = metric_from_name(cdistname, namelen);
-  if (metric < 0) {  // libext.rs:520-523: unknown distance => null
-    set_err("unknown distance name '" + std::string((const char*)cdistname, namelen) + "'");
+  if (metric < 0 || !hb::metric_supported(metric, dtype)) {  // libext.rs:520-523: unknown distance => null
+    set_err("unknown / unsupported distance name '" + std::string((const char*)cdistname, namelen) + "' for this element type");
     return nullptr;
   }
   if (max_nb_conn < 2 || max_nb_conn > 256) {  // hnsw.rs:784-787 caps at 256; ln(1) = 0 breaks the level law
@@ -63,40 +69,20 @@ static const HnswApif32* make_index(size_t max_nb_conn, size_t ef_const, size_t 
     set_err("ef_construction and max_layer must be positive");
     return nullptr;
   }
-  Index* ix = new Index((int)max_nb_conn, max_elements, (int)max_layer, (int)ef_const, metric, g_device);
+  Index* ix = new Index((int)max_nb_conn, max_elements, (int)max_layer, (int)ef_const, metric, dtype, g_device);
   if (!ix->ok()) {
     set_err(ix->err());
     delete ix;
     return nullptr;
   }
-  return new HnswApif32{ix};
+  return new AnyApi{ix};
 }
 
-extern "C" {
-
-const HnswApif32* init_hnsw_f32(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname) {
-  return make_index(max_nb_conn, ef_const, namelen, cdistname, 10000, 16);  // libext.rs:470-518
-}
-
-const HnswApif32* new_hnsw_f32(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname,
-                               size_t max_elements, size_t max_layer) {
-  return make_index(max_nb_conn, ef_const, namelen, cdistname, max_elements, max_layer);
-}
-
-void drop_hnsw_f32(const HnswApif32* p) {
-  if (!p) return;
-  delete p->ix;
-  delete p;
-}
-
-const HnswApif32* init_hnsw_ptrdist_f32(size_t, size_t, float (*)(const float*, const float*, unsigned long long)) {
-  set_err("init_hnsw_ptrdist_f32: a host distance callback cannot run inside a CUDA kernel; use a named distance");
-  return nullptr;
-}
-
-void insert_f32(HnswApif32* h, size_t len, const float* data, size_t id) {
+// ---- generic bodies of the reference entry points (element type = the handle's)
+static void insert_any(void* hv, size_t len, const void* data, size_t id) {
+  AnyApi* h = (AnyApi*)hv;
   if (!h || !data) {
-    set_err("insert_f32: NULL argument");
+    set_err("insert: NULL argument");
     return;
   }
   std::lock_guard<std::mutex> g(h->ix->mu);
@@ -105,9 +91,10 @@ void insert_f32(HnswApif32* h, size_t len, const float* data, size_t id) {
   pass(h->ix, h->ix->insert_batch(data, 1, len, nullptr, &id64, nullptr));
 }
 
-void parallel_insert_f32(HnswApif32* h, size_t nb_vec, size_t vec_len, const float** datas, const size_t* ids) {
+static void parallel_insert_any(void* hv, size_t nb_vec, size_t vec_len, const void* const* datas, const size_t* ids) {
+  AnyApi* h = (AnyApi*)hv;
   if (!h || !datas || !ids) {
-    set_err("parallel_insert_f32: NULL argument");
+    set_err("parallel_insert: NULL argument");
     return;
   }
   std::lock_guard<std::mutex> g(h->ix->mu);
@@ -116,10 +103,10 @@ void parallel_insert_f32(HnswApif32* h, size_t nb_vec, size_t vec_len, const flo
   pass(h->ix, h->ix->insert_batch(nullptr, nb_vec, vec_len, datas, id64.data(), nullptr));
 }
 
-const Neighbourhood_api* search_neighbours_f32(const HnswApif32* h, size_t len, const float* data, size_t knbn,
-                                               size_t ef_search) {
+static const Neighbourhood_api* search_any(const void* hv, size_t len, const void* data, size_t knbn, size_t ef_search) {
+  const AnyApi* h = (const AnyApi*)hv;
   if (!h || !data || knbn == 0) {
-    set_err("search_neighbours_f32: bad argument");
+    set_err("search_neighbours: bad argument");
     return nullptr;
   }
   std::lock_guard<std::mutex> g(h->ix->mu);
@@ -141,10 +128,11 @@ struct VecApiBox {
   Neighbour_api* block;
 };
 
-const Vec_api_Neighbourhood_api* parallel_search_neighbours_f32(const HnswApif32* h, size_t nb_vec, int64_t vec_len,
-                                                                const float** data, size_t knbn, size_t ef_search) {
+static const Vec_api_Neighbourhood_api* parallel_search_any(const void* hv, size_t nb_vec, int64_t vec_len,
+                                                            const void* const* data, size_t knbn, size_t ef_search) {
+  const AnyApi* h = (const AnyApi*)hv;
   if (!h || (!data && nb_vec) || knbn == 0) {
-    set_err("parallel_search_neighbours_f32: bad argument");
+    set_err("parallel_search_neighbours: bad argument");
     return nullptr;
   }
   std::lock_guard<std::mutex> g(h->ix->mu);
@@ -168,11 +156,81 @@ const Vec_api_Neighbourhood_api* parallel_search_neighbours_f32(const HnswApif32
   return &box->v;
 }
 
-int64_t file_dump_f32(const HnswApif32* h, size_t, const uint8_t*) {
-  (void)h;
-  set_err("file_dump_f32: the .hnsw.graph/.hnsw.data writer is SURVEY §8 row f2 (next), not built yet");
+static void drop_any(const void* p) {
+  const AnyApi* h = (const AnyApi*)p;
+  if (!h) return;
+  delete h->ix;
+  delete h;
+}
+
+static int64_t file_dump_any(const void* hv, size_t namelen, const uint8_t* filename);
+
+extern "C" {
+
+// libext.rs generates one set of entry points per element type with macros (generate_insert!, ... :106-275,
+// instantiated :770-771, 829-835, 898-904, 1044-1048, 1112-1116); so do we.
+#define HB_TYPED_API(SUF, CT, DT)                                                                                      \
+  const HnswApi##SUF* init_hnsw_##SUF(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname) { \
+    return (const HnswApi##SUF*)make_index(DT, max_nb_conn, ef_const, namelen, cdistname, 10000, 16);                   \
+  }                                                                                                                    \
+  const HnswApi##SUF* init_hnsw_ptrdist_##SUF(size_t, size_t, float (*)(const CT*, const CT*, unsigned long long)) {   \
+    set_err("init_hnsw_ptrdist: a host distance callback cannot run inside a CUDA kernel; use a named distance");      \
+    return nullptr;                                                                                                    \
+  }                                                                                                                    \
+  void insert_##SUF(HnswApi##SUF* h, size_t len, const CT* data, size_t id) { insert_any(h, len, data, id); }          \
+  void parallel_insert_##SUF(HnswApi##SUF* h, size_t nb_vec, size_t vec_len, const CT** datas, const size_t* ids) {    \
+    parallel_insert_any(h, nb_vec, vec_len, (const void* const*)datas, ids);                                           \
+  }                                                                                                                    \
+  const Neighbourhood_api* search_neighbours_##SUF(const HnswApi##SUF* h, size_t len, const CT* data, size_t knbn,     \
+                                                   size_t ef_search) {                                                 \
+    return search_any(h, len, data, knbn, ef_search);                                                                  \
+  }                                                                                                                    \
+  const Vec_api_Neighbourhood_api* parallel_search_neighbours_##SUF(const HnswApi##SUF* h, size_t nb_vec,              \
+                                                                    int64_t vec_len, const CT** data, size_t knbn,     \
+                                                                    size_t ef_search) {                                \
+    return parallel_search_any(h, nb_vec, vec_len, (const void* const*)data, knbn, ef_search);                         \
+  }                                                                                                                    \
+  int64_t file_dump_##SUF(const HnswApi##SUF* h, size_t namelen, const uint8_t* filename) {                            \
+    return file_dump_any(h, namelen, filename);                                                                        \
+  }
+
+HB_TYPED_API(f32, float, hb::DT_F32)
+HB_TYPED_API(i32, int32_t, hb::DT_I32)
+HB_TYPED_API(u32, uint32_t, hb::DT_U32)
+HB_TYPED_API(u16, uint16_t, hb::DT_U16)
+HB_TYPED_API(u8, uint8_t, hb::DT_U8)
+#undef HB_TYPED_API
+
+const HnswApif32* new_hnsw_f32(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname,
+                               size_t max_elements, size_t max_layer) {
+  return (const HnswApif32*)make_index(hb::DT_F32, max_nb_conn, ef_const, namelen, cdistname, max_elements, max_layer);
+}
+const HnswApiu16* new_hnsw_u16(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname,
+                               size_t max_elements, size_t max_layer) {  // libext.rs:964-1028
+  return (const HnswApiu16*)make_index(hb::DT_U16, max_nb_conn, ef_const, namelen, cdistname, max_elements, max_layer);
+}
+void drop_hnsw_f32(const HnswApif32* p) { drop_any(p); }  // libext.rs:626-630
+void drop_hnsw_u16(const HnswApiu16* p) { drop_any(p); }  // libext.rs:636-640
+void hnsw_b200_drop(const void* p) { drop_any(p); }       // upstream exports no drop for i32/u32/u8
+// typed constructor with max_elements / max_layer for every element type (upstream has it for f32 and u16 only)
+void* hnsw_b200_new(int dtype, size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname,
+                    size_t max_elements, size_t max_layer) {
+  if (dtype < 0 || dtype > 4) {
+    set_err("dtype must be 0 f32, 1 u8, 2 u16, 3 u32, 4 i32");
+    return nullptr;
+  }
+  return make_index(dtype, max_nb_conn, ef_const, namelen, cdistname, max_elements, max_layer);
+}
+
+}  // extern "C"
+
+static int64_t file_dump_any(const void* hv, size_t, const uint8_t*) {
+  (void)hv;
+  set_err("file_dump: the .hnsw.graph/.hnsw.data writer is SURVEY §8 row f2 (next), not built yet");
   return -1;
 }
+
+extern "C" {
 
 void init_rust_log(void) {}
 
@@ -208,10 +266,10 @@ void hnsw_b200_free_vec_api(const Vec_api_Neighbourhood_api* p) {
 
 #define HB_H(h) \
   if (!(h)) return set_err("NULL handle"); \
-  Index* ix = (h)->ix;                     \
+  Index* ix = ((const AnyApi*)(h))->ix;    \
   std::lock_guard<std::mutex> g__(ix->mu)
 
-int hnsw_b200_set_extend_candidates(HnswApif32* h, int flag) {
+int hnsw_b200_set_extend_candidates(void* h, int flag) {
   HB_H(h);
   if (flag && ix->ef_c <= 2 * ix->M)
     return set_err("extend_candidates needs ef_construction > 2*max_nb_connection in this engine (otherwise the "
@@ -219,32 +277,32 @@ int hnsw_b200_set_extend_candidates(HnswApif32* h, int flag) {
   ix->extend_candidates = flag != 0;
   return 0;
 }
-int hnsw_b200_set_keeping_pruned(HnswApif32* h, int flag) {
+int hnsw_b200_set_keeping_pruned(void* h, int flag) {
   HB_H(h);
   ix->keep_pruned = flag != 0;
   return 0;
 }
-int hnsw_b200_modify_level_scale(HnswApif32* h, double scale) {
+int hnsw_b200_modify_level_scale(void* h, double scale) {
   HB_H(h);
   if (ix->n > 0) return set_err("modify_level_scale: index already holds points (hnsw.rs:881-888)");
   if (!(scale >= 0.2 && scale <= 1.0)) return set_err("modify_level_scale: factor must be in [0.2, 1]");  // hnsw.rs:889-900
   ix->level_scale = scale / std::log((double)ix->M);
   return 0;
 }
-int hnsw_b200_set_searching_mode(HnswApif32* h, int flag) {
+int hnsw_b200_set_searching_mode(void* h, int flag) {
   HB_H(h);
   ix->searching = flag != 0;
   return 0;
 }
-int hnsw_b200_set_level_seed(HnswApif32* h, uint64_t seed) {
+int hnsw_b200_set_level_seed(void* h, uint64_t seed) {
   HB_H(h);
   ix->rng.s = seed;
   return 0;
 }
-uint64_t hnsw_b200_get_nb_point(const HnswApif32* h) { return h ? h->ix->n : 0; }
-int hnsw_b200_get_max_level_observed(const HnswApif32* h) { return h ? std::max(h->ix->entry_level, 0) : 0; }
-int hnsw_b200_get_dim(const HnswApif32* h) { return h ? h->ix->dim : 0; }
-int hnsw_b200_set_insert_batching(HnswApif32* h, uint32_t ratio, uint32_t max_batch) {
+uint64_t hnsw_b200_get_nb_point(const void* h) { return h ? ((const AnyApi*)h)->ix->n : 0; }
+int hnsw_b200_get_max_level_observed(const void* h) { return h ? std::max(((const AnyApi*)h)->ix->entry_level, 0) : 0; }
+int hnsw_b200_get_dim(const void* h) { return h ? ((const AnyApi*)h)->ix->dim : 0; }
+int hnsw_b200_set_insert_batching(void* h, uint32_t ratio, uint32_t max_batch) {
   HB_H(h);
   if (ratio == 0 || max_batch == 0) return set_err("ratio and max_batch must be positive");
   ix->batch_ratio = ratio;
@@ -252,7 +310,7 @@ int hnsw_b200_set_insert_batching(HnswApif32* h, uint32_t ratio, uint32_t max_ba
   return 0;
 }
 
-int hnsw_b200_insert_flat(HnswApif32* h, const float* vecs, uint64_t n, uint64_t dim, const uint64_t* ids,
+int hnsw_b200_insert_flat(void* h, const void* vecs, uint64_t n, uint64_t dim, const uint64_t* ids,
                           const int32_t* levels) {
   HB_H(h);
   if (n == 0) return 0;
@@ -262,7 +320,7 @@ int hnsw_b200_insert_flat(HnswApif32* h, const float* vecs, uint64_t n, uint64_t
   return pass(ix, ix->insert_batch(vecs, n, dim, nullptr, ids, levels));
 }
 
-int hnsw_b200_search_flat(const HnswApif32* h, const float* queries, uint64_t nq, uint64_t dim, uint64_t knbn,
+int hnsw_b200_search_flat(const void* h, const void* queries, uint64_t nq, uint64_t dim, uint64_t knbn,
                           uint64_t ef_search, int filter_mode, const uint64_t* filter_ids, uint64_t nfilter,
                           hnsw_b200_filter_fn fn, void* ctx, uint64_t* out_ids, float* out_dist,
                           uint32_t* out_internal, int32_t* out_pid, int32_t* out_counts) {
@@ -294,34 +352,34 @@ int hnsw_b200_search_flat(const HnswApif32* h, const float* queries, uint64_t nq
   return 0;
 }
 
-int hnsw_b200_search_device(const HnswApif32* h, const float* d_queries, uint64_t nq, uint64_t knbn,
+int hnsw_b200_search_device(const void* h, const void* d_queries, uint64_t nq, uint64_t knbn,
                             uint64_t ef_search, void* d_out, int32_t* d_counts, int sync, float* kernel_ms) {
   HB_H(h);
   return pass(ix, ix->search_device(d_queries, nq, knbn, ef_search, nullptr, (NeighbourOut*)d_out, d_counts, sync != 0,
                                     kernel_ms));
 }
 
-int hnsw_b200_set_stream(HnswApif32* h, void* cuda_stream) {
+int hnsw_b200_set_stream(void* h, void* cuda_stream) {
   HB_H(h);
   return pass(ix, ix->set_stream((cudaStream_t)cuda_stream));
 }
-int hnsw_b200_check_status(HnswApif32* h) {
+int hnsw_b200_check_status(void* h) {
   HB_H(h);
   int r = ix->check_status();
   if (r < 0) g_err = ix->err();
   return r;
 }
 
-int hnsw_b200_enable_stats(HnswApif32* h, int enable) {
+int hnsw_b200_enable_stats(void* h, int enable) {
   HB_H(h);
   return ix->enable_stats(enable != 0);
 }
-int hnsw_b200_get_stats(const HnswApif32* h, uint64_t* out4, int reset) {
+int hnsw_b200_get_stats(const void* h, uint64_t* out4, int reset) {
   HB_H(h);
   return pass(ix, ix->get_stats(out4, reset != 0));
 }
 
-int hnsw_b200_export_points(const HnswApif32* h, uint8_t* levels, int32_t* ranks, uint64_t* origin, int64_t* entry) {
+int hnsw_b200_export_points(const void* h, uint8_t* levels, int32_t* ranks, uint64_t* origin, int64_t* entry) {
   HB_H(h);
   for (size_t i = 0; i < ix->n; ++i) {
     if (levels) levels[i] = ix->h_level[i];
@@ -331,53 +389,53 @@ int hnsw_b200_export_points(const HnswApif32* h, uint8_t* levels, int32_t* ranks
   if (entry) *entry = ix->entry == hb::INVALID_ID ? -1 : (int64_t)ix->entry;
   return 0;
 }
-int hnsw_b200_export_vectors(const HnswApif32* h, float* out) {
+int hnsw_b200_export_vectors(const void* h, void* out) {
   HB_H(h);
   return pass(ix, ix->export_vectors(out));
 }
-int64_t hnsw_b200_layer_edges(const HnswApif32* h, int layer) {
+int64_t hnsw_b200_layer_edges(const void* h, int layer) {
   if (!h) return set_err("NULL handle");
-  Index* ix = h->ix;
+  Index* ix = ((const AnyApi*)h)->ix;
   std::lock_guard<std::mutex> g(ix->mu);
   int64_t total = 0;
   if (pass(ix, ix->export_layer(layer, nullptr, nullptr, nullptr, &total))) return -1;
   return total;
 }
-int hnsw_b200_export_layer(const HnswApif32* h, int layer, uint64_t* offsets, uint32_t* ids, float* dists) {
+int hnsw_b200_export_layer(const void* h, int layer, uint64_t* offsets, uint32_t* ids, float* dists) {
   HB_H(h);
   return pass(ix, ix->export_layer(layer, offsets, ids, dists, nullptr));
 }
-int hnsw_b200_import_graph(HnswApif32* h, const float* vecs, uint64_t n, uint64_t dim, const uint64_t* origin,
+int hnsw_b200_import_graph(void* h, const void* vecs, uint64_t n, uint64_t dim, const uint64_t* origin,
                            const uint8_t* levels, int64_t entry, int nlayers, const uint64_t* const* offsets,
                            const uint32_t* const* ids, const float* const* dists) {
   HB_H(h);
   return pass(ix, ix->import_graph(vecs, n, (int)dim, origin, levels, entry, nlayers, offsets, ids, dists));
 }
 
-int hnsw_b200_blob_header(const HnswApif32* h, uint64_t* header16) {
+int hnsw_b200_blob_header(const void* h, uint64_t* header16) {
   HB_H(h);
   return ix->blob_header(header16);
 }
-int hnsw_b200_blob_alloc(HnswApif32* h, const uint64_t* header16) {
+int hnsw_b200_blob_alloc(void* h, const uint64_t* header16) {
   HB_H(h);
   return pass(ix, ix->blob_alloc(header16));
 }
-int hnsw_b200_blob_count(const HnswApif32* h) { return h ? h->ix->blob_count() : 0; }
-int hnsw_b200_blob_info(const HnswApif32* h, int i, void** dev_ptr, uint64_t* nbytes) {
+int hnsw_b200_blob_count(const void* h) { return h ? ((const AnyApi*)h)->ix->blob_count() : 0; }
+int hnsw_b200_blob_info(const void* h, int i, void** dev_ptr, uint64_t* nbytes) {
   HB_H(h);
   return pass(ix, ix->blob_info(i, dev_ptr, nbytes));
 }
-int hnsw_b200_blob_commit(HnswApif32* h) {
+int hnsw_b200_blob_commit(void* h) {
   HB_H(h);
   return pass(ix, ix->blob_commit());
 }
 
-int hnsw_b200_dist_batch(const HnswApif32* h, const float* queries, uint64_t nq, uint64_t dim, const uint32_t* cand,
+int hnsw_b200_dist_batch(const void* h, const void* queries, uint64_t nq, uint64_t dim, const uint32_t* cand,
                          uint64_t m, float* out) {
   HB_H(h);
   return pass(ix, ix->dist_batch(queries, nq, (int)dim, cand, m, out));
 }
-int hnsw_b200_bruteforce(const HnswApif32* h, const float* queries, uint64_t nq, uint64_t dim, uint64_t k,
+int hnsw_b200_bruteforce(const void* h, const void* queries, uint64_t nq, uint64_t dim, uint64_t k,
                          uint32_t* out_ids, float* out_dist) {
   HB_H(h);
   return pass(ix, ix->bruteforce(queries, nq, (int)dim, k, out_ids, out_dist));

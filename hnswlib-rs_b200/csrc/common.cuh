@@ -39,8 +39,9 @@ enum Metric : int {
 // up_off[id] in adjU (list for layer l is up_off[id] + l - 1).  plevel >= level; it exceeds the
 // point's own level only for former entry points (see DESIGN.md "lists above a point's level").
 struct GraphView {
-  const float* vec;
-  int d4;  // float4 per row = d_pad / 4 (multiple of 8)
+  const void* vec;  // rows of element type T (f32, i32, u32, u16, u8), zero padded to whole 128-byte lines
+  int d4;           // 16-byte chunks per row (multiple of 8)
+  int dim;          // true number of elements per vector
   uint32_t* adj0;
   float* adj0_d;
   int deg0;
@@ -85,21 +86,39 @@ struct OpL2 {
     a = __fmaf_rn(df, df, a);
   }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
-  static __device__ __forceinline__ float finish(acc_t a) { return __fsqrt_rn(a); }
+  static __device__ __forceinline__ float finish(acc_t a, int) { return __fsqrt_rn(a); }
+  static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
+    step(a, __uint_as_float(q.x), __uint_as_float(x.x));
+    step(a, __uint_as_float(q.y), __uint_as_float(x.y));
+    step(a, __uint_as_float(q.z), __uint_as_float(x.z));
+    step(a, __uint_as_float(q.w), __uint_as_float(x.w));
+  }
 };
 struct OpL1 {
   typedef float acc_t;
   static __device__ __forceinline__ acc_t zero() { return 0.f; }
   static __device__ __forceinline__ void step(acc_t& a, float q, float x) { a = __fadd_rn(a, fabsf(__fsub_rn(q, x))); }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
-  static __device__ __forceinline__ float finish(acc_t a) { return a; }
+  static __device__ __forceinline__ float finish(acc_t a, int) { return a; }
+  static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
+    step(a, __uint_as_float(q.x), __uint_as_float(x.x));
+    step(a, __uint_as_float(q.y), __uint_as_float(x.y));
+    step(a, __uint_as_float(q.z), __uint_as_float(x.z));
+    step(a, __uint_as_float(q.w), __uint_as_float(x.w));
+  }
 };
 struct OpDot {
   typedef float acc_t;
   static __device__ __forceinline__ acc_t zero() { return 0.f; }
   static __device__ __forceinline__ void step(acc_t& a, float q, float x) { a = __fmaf_rn(q, x, a); }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
-  static __device__ __forceinline__ float finish(acc_t a) { return fmaxf(__fsub_rn(1.0f, a), 0.f); }
+  static __device__ __forceinline__ float finish(acc_t a, int) { return fmaxf(__fsub_rn(1.0f, a), 0.f); }
+  static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
+    step(a, __uint_as_float(q.x), __uint_as_float(x.x));
+    step(a, __uint_as_float(q.y), __uint_as_float(x.y));
+    step(a, __uint_as_float(q.z), __uint_as_float(x.z));
+    step(a, __uint_as_float(q.w), __uint_as_float(x.w));
+  }
 };
 struct Cos3 {
   double ab, aa, bb;
@@ -120,12 +139,18 @@ struct OpCosine {  // f64 accumulation like anndists DistCosine
     r.bb = __dadd_rn(a.bb, __shfl_xor_sync(FULL, a.bb, off));
     return r;
   }
-  static __device__ __forceinline__ float finish(acc_t a) {
+  static __device__ __forceinline__ float finish(acc_t a, int) {
     if (a.aa > 0. && a.bb > 0.) {
       double r = __dsub_rn(1., __ddiv_rn(a.ab, __dsqrt_rn(__dmul_rn(a.aa, a.bb))));
       return (float)(r > 0. ? r : 0.);
     }
     return 0.f;
+  }
+  static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
+    step(a, __uint_as_float(q.x), __uint_as_float(x.x));
+    step(a, __uint_as_float(q.y), __uint_as_float(x.y));
+    step(a, __uint_as_float(q.z), __uint_as_float(x.z));
+    step(a, __uint_as_float(q.w), __uint_as_float(x.w));
   }
 };
 struct OpHellinger {
@@ -133,7 +158,13 @@ struct OpHellinger {
   static __device__ __forceinline__ acc_t zero() { return 0.f; }
   static __device__ __forceinline__ void step(acc_t& a, float q, float x) { a = __fadd_rn(a, __fsqrt_rn(__fmul_rn(q, x))); }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
-  static __device__ __forceinline__ float finish(acc_t a) { return __fsqrt_rn(fmaxf(__fsub_rn(1.0f, a), 0.f)); }
+  static __device__ __forceinline__ float finish(acc_t a, int) { return __fsqrt_rn(fmaxf(__fsub_rn(1.0f, a), 0.f)); }
+  static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
+    step(a, __uint_as_float(q.x), __uint_as_float(x.x));
+    step(a, __uint_as_float(q.y), __uint_as_float(x.y));
+    step(a, __uint_as_float(q.z), __uint_as_float(x.z));
+    step(a, __uint_as_float(q.w), __uint_as_float(x.w));
+  }
 };
 struct OpJeffreys {
   typedef float acc_t;
@@ -143,7 +174,13 @@ struct OpJeffreys {
     a = __fadd_rn(a, __fmul_rn(__fsub_rn(q, x), logf(__fdiv_rn(qm, xm))));
   }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
-  static __device__ __forceinline__ float finish(acc_t a) { return a; }
+  static __device__ __forceinline__ float finish(acc_t a, int) { return a; }
+  static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
+    step(a, __uint_as_float(q.x), __uint_as_float(x.x));
+    step(a, __uint_as_float(q.y), __uint_as_float(x.y));
+    step(a, __uint_as_float(q.z), __uint_as_float(x.z));
+    step(a, __uint_as_float(q.w), __uint_as_float(x.w));
+  }
 };
 struct OpJS {
   typedef float acc_t;
@@ -156,23 +193,115 @@ struct OpJS {
     a = __fadd_rn(a, t);
   }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
-  static __device__ __forceinline__ float finish(acc_t a) { return __fsqrt_rn(fmaxf(__fmul_rn(0.5f, a), 0.f)); }
+  static __device__ __forceinline__ float finish(acc_t a, int) { return __fsqrt_rn(fmaxf(__fmul_rn(0.5f, a), 0.f)); }
+  static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
+    step(a, __uint_as_float(q.x), __uint_as_float(x.x));
+    step(a, __uint_as_float(q.y), __uint_as_float(x.y));
+    step(a, __uint_as_float(q.z), __uint_as_float(x.z));
+    step(a, __uint_as_float(q.w), __uint_as_float(x.w));
+  }
+};
+
+// ---- integer element types: a 16-byte chunk holds 4 (i32/u32), 8 (u16) or 16 (u8) elements.
+// L1/L2 cast every element to f32 (as anndists does for integer T) and accumulate like the f32 ops, elements of a
+// chunk in memory order.  Hamming counts differing elements, Jaccard sums min and max, both in exact integers.
+template <class T>
+struct Elems;
+template <>
+struct Elems<uint32_t> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ float get(const uint4& v, int i) { return (float)(i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w); }
+};
+template <>
+struct Elems<int32_t> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ float get(const uint4& v, int i) { return (float)(int32_t)(i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w); }
+};
+template <>
+struct Elems<uint16_t> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ float get(const uint4& v, int i) {
+    const uint32_t w = (i >> 1) == 0 ? v.x : (i >> 1) == 1 ? v.y : (i >> 1) == 2 ? v.z : v.w;
+    return (float)((w >> (16 * (i & 1))) & 0xFFFFu);
+  }
+};
+template <>
+struct Elems<uint8_t> {
+  static constexpr int N = 16;
+  static __device__ __forceinline__ float get(const uint4& v, int i) {
+    const uint32_t w = (i >> 2) == 0 ? v.x : (i >> 2) == 1 ? v.y : (i >> 2) == 2 ? v.z : v.w;
+    return (float)((w >> (8 * (i & 3))) & 0xFFu);
+  }
+};
+
+template <class T, class FOp>  // FOp = OpL1 / OpL2 on the elements cast to f32
+struct OpCast {
+  typedef float acc_t;
+  static __device__ __forceinline__ acc_t zero() { return 0.f; }
+  static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
+#pragma unroll
+    for (int i = 0; i < Elems<T>::N; ++i) FOp::step(a, Elems<T>::get(q, i), Elems<T>::get(x, i));
+  }
+  static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return FOp::comb(a, off); }
+  static __device__ __forceinline__ float finish(acc_t a, int d) { return FOp::finish(a, d); }
+};
+
+template <class T>
+struct OpHamming {  // DistHamming: #{a_i != b_i} / len
+  typedef uint32_t acc_t;
+  static __device__ __forceinline__ acc_t zero() { return 0u; }
+  static __device__ __forceinline__ uint32_t ne(uint32_t a, uint32_t b) {
+    if (sizeof(T) == 1) return __popc(__vcmpne4(a, b) & 0x01010101u);
+    if (sizeof(T) == 2) return __popc(__vcmpne2(a, b) & 0x00010001u);
+    return a != b ? 1u : 0u;
+  }
+  static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
+    a += ne(q.x, x.x) + ne(q.y, x.y) + ne(q.z, x.z) + ne(q.w, x.w);
+  }
+  static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return a + __shfl_xor_sync(FULL, a, off); }
+  static __device__ __forceinline__ float finish(acc_t a, int d) { return __fdiv_rn((float)a, (float)d); }
+};
+
+struct MinMax64 {
+  unsigned long long mn, mx;
+};
+template <class T>
+struct OpJaccard {  // weighted Jaccard: 1 - sum min / sum max, integer sums, f64 division
+  typedef MinMax64 acc_t;
+  static __device__ __forceinline__ acc_t zero() { return MinMax64{0ull, 0ull}; }
+  static __device__ __forceinline__ void word(acc_t& a, uint32_t q, uint32_t x) {
+    if (sizeof(T) == 1) {
+      a.mn += __vsadu4(__vminu4(q, x), 0u);
+      a.mx += __vsadu4(__vmaxu4(q, x), 0u);
+    } else if (sizeof(T) == 2) {
+      a.mn += __vsadu2(__vminu2(q, x), 0u);
+      a.mx += __vsadu2(__vmaxu2(q, x), 0u);
+    } else {
+      a.mn += q < x ? q : x;
+      a.mx += q < x ? x : q;
+    }
+  }
+  static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
+    word(a, q.x, x.x);
+    word(a, q.y, x.y);
+    word(a, q.z, x.z);
+    word(a, q.w, x.w);
+  }
+  static __device__ __forceinline__ acc_t comb(acc_t a, int off) {
+    return MinMax64{a.mn + __shfl_xor_sync(FULL, a.mn, off), a.mx + __shfl_xor_sync(FULL, a.mx, off)};
+  }
+  static __device__ __forceinline__ float finish(acc_t a, int) {
+    if (a.mx == 0ull) return 0.f;
+    return (float)__dsub_rn(1.0, __ddiv_rn((double)a.mn, (double)a.mx));
+  }
 };
 
 template <class Op>
-__device__ __forceinline__ void step4(typename Op::acc_t& a, const float4& q, const float4& x) {
-  Op::step(a, q.x, x.x);
-  Op::step(a, q.y, x.y);
-  Op::step(a, q.z, x.z);
-  Op::step(a, q.w, x.w);
-}
-
-template <class Op>
-__device__ __forceinline__ float reduce8(typename Op::acc_t a) {
+__device__ __forceinline__ float reduce8(typename Op::acc_t a, int dim) {
   a = Op::comb(a, 4);
   a = Op::comb(a, 2);
   a = Op::comb(a, 1);
-  return Op::finish(a);
+  return Op::finish(a, dim);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -181,23 +310,23 @@ __device__ __forceinline__ float reduce8(typename Op::acc_t a) {
 // U passes in flight; CH = d4/8 when known at compile time (CH float4 loads per lane per row),
 // CH = 0 for the generic loop.  Every load instruction covers 4 rows x 128 B contiguous.
 template <class Op, int CH, int U>
-__device__ __forceinline__ void warp_dists(const float4* __restrict__ vec, int d4, const float4* q4, const uint32_t* ids,
-                                           int n, float* out) {
+__device__ __forceinline__ void warp_dists(const uint4* __restrict__ vec, int d4, int dim, const uint4* q4,
+                                           const uint32_t* ids, int n, float* out) {
   const int lane = lane_id();
   const int g = lane & 7, r = lane >> 3;
   if constexpr (CH > 0) {
-    float4 qv[CH];
+    uint4 qv[CH];
 #pragma unroll
     for (int i = 0; i < CH; ++i) qv[i] = q4[g + 8 * i];
     for (int base = 0; base < n; base += 4 * U) {
-      const float4* row[U];
+      const uint4* row[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         int idx = base + u * 4 + r;
         uint32_t id = ids[idx < n ? idx : n - 1];
         row[u] = vec + (size_t)id * d4 + g;
       }
-      float4 x[U][CH];
+      uint4 x[U][CH];
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -206,8 +335,8 @@ __device__ __forceinline__ void warp_dists(const float4* __restrict__ vec, int d
       for (int u = 0; u < U; ++u) {
         typename Op::acc_t a = Op::zero();
 #pragma unroll
-        for (int i = 0; i < CH; ++i) step4<Op>(a, qv[i], x[u][i]);
-        float dist = reduce8<Op>(a);
+        for (int i = 0; i < CH; ++i) Op::chunk(a, qv[i], x[u][i]);
+        float dist = reduce8<Op>(a, dim);
         int idx = base + u * 4 + r;
         if (g == 0 && idx < n) out[idx] = dist;
       }
@@ -215,7 +344,7 @@ __device__ __forceinline__ void warp_dists(const float4* __restrict__ vec, int d
   } else {
     const int nch = d4 >> 3;
     for (int base = 0; base < n; base += 4 * U) {
-      const float4* row[U];
+      const uint4* row[U];
       typename Op::acc_t a[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -226,21 +355,41 @@ __device__ __forceinline__ void warp_dists(const float4* __restrict__ vec, int d
       }
 #pragma unroll 4
       for (int i = 0; i < nch; ++i) {
-        float4 qv = q4[g + 8 * i];
+        uint4 qv = q4[g + 8 * i];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          float4 x = __ldg(row[u] + 8 * i);
-          step4<Op>(a[u], qv, x);
+          uint4 x = __ldg(row[u] + 8 * i);
+          Op::chunk(a[u], qv, x);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        float dist = reduce8<Op>(a[u]);
+        float dist = reduce8<Op>(a[u], dim);
         int idx = base + u * 4 + r;
         if (g == 0 && idx < n) out[idx] = dist;
       }
     }
   }
+}
+
+// copy one query/point row of `nbytes` raw bytes into the warp's shared-memory row buffer, zero padding to row_bytes
+__device__ __forceinline__ void stage_row_bytes(void* dst, const void* src, int nbytes, int row_bytes) {
+  const int lane = lane_id();
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+  const int nw = nbytes >> 2;
+  if ((reinterpret_cast<size_t>(src) & 3) == 0) {
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+    for (int i = lane; i < (row_bytes >> 2); i += 32) d32[i] = i < nw ? s32[i] : 0u;
+    __syncwarp();
+    const uint8_t* s8 = reinterpret_cast<const uint8_t*>(src);
+    uint8_t* d8 = reinterpret_cast<uint8_t*>(dst);
+    for (int i = (nw << 2) + lane; i < nbytes; i += 32) d8[i] = s8[i];
+  } else {
+    const uint8_t* s8 = reinterpret_cast<const uint8_t*>(src);
+    uint8_t* d8 = reinterpret_cast<uint8_t*>(dst);
+    for (int i = lane; i < row_bytes; i += 32) d8[i] = i < nbytes ? s8[i] : (uint8_t)0;
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -276,7 +425,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 constexpr int STAGE_ROWS = 8;  // rows of a chunk fetched by TMA; the rest of the chunk goes through registers
 
 struct Stage {
-  float4* buf;    // [STAGE_ROWS][d4] or nullptr (rows too long to stage)
+  uint4* buf;    // [STAGE_ROWS][d4] or nullptr (rows too long to stage)
   uint64_t* bar;  // mbarrier, arrival count 1
   uint32_t phase;
 };
@@ -285,10 +434,10 @@ struct Stage {
 // all in flight together; then the staged rows are reduced from shared memory with the same lane/chunk mapping,
 // so every distance is bit-identical to the pure register path.
 template <class Op, int CH, int U>
-__device__ __forceinline__ void warp_dists_staged(const float4* __restrict__ vec, int d4, const float4* q4,
+__device__ __forceinline__ void warp_dists_staged(const uint4* __restrict__ vec, int d4, int dim, const uint4* q4,
                                                   const uint32_t* ids, int n, float* out, Stage& st) {
   if constexpr (CH == 0) {
-    warp_dists<Op, CH, U>(vec, d4, q4, ids, n, out);
+    warp_dists<Op, CH, U>(vec, d4, dim, q4, ids, n, out);
   } else {
     const int lane = lane_id();
     const int nst = n < STAGE_ROWS ? n : STAGE_ROWS;
@@ -297,9 +446,9 @@ __device__ __forceinline__ void warp_dists_staged(const float4* __restrict__ vec
     if (lane == 0) mbar_expect_tx(st.bar, row_bytes * nst);
     __syncwarp();
     if (lane < nst) bulk_g2s(st.buf + (size_t)lane * d4, vec + (size_t)ids[lane] * d4, row_bytes, st.bar);
-    if (n > STAGE_ROWS) warp_dists<Op, CH, U>(vec, d4, q4, ids + STAGE_ROWS, n - STAGE_ROWS, out + STAGE_ROWS);
+    if (n > STAGE_ROWS) warp_dists<Op, CH, U>(vec, d4, dim, q4, ids + STAGE_ROWS, n - STAGE_ROWS, out + STAGE_ROWS);
     const int g = lane & 7, r = lane >> 3;
-    float4 qv[CH];
+    uint4 qv[CH];
 #pragma unroll
     for (int i = 0; i < CH; ++i) qv[i] = q4[g + 8 * i];
     mbar_wait(st.bar, st.phase);
@@ -308,14 +457,14 @@ __device__ __forceinline__ void warp_dists_staged(const float4* __restrict__ vec
     for (int pass = 0; pass < STAGE_ROWS / 4; ++pass) {
       const int row = pass * 4 + r;
       if (pass * 4 < nst) {
-        const float4* src = st.buf + (size_t)(row < nst ? row : nst - 1) * d4 + g;
+        const uint4* src = st.buf + (size_t)(row < nst ? row : nst - 1) * d4 + g;
         typename Op::acc_t a = Op::zero();
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
-          const float4 x = src[8 * i];
-          step4<Op>(a, qv[i], x);
+          const uint4 x = src[8 * i];
+          Op::chunk(a, qv[i], x);
         }
-        const float dist = reduce8<Op>(a);
+        const float dist = reduce8<Op>(a, dim);
         if (g == 0 && row < nst) out[row] = dist;
       }
     }

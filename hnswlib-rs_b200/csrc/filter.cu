@@ -24,11 +24,11 @@ __device__ __forceinline__ void search_layer_filtered(const GraphView& g, const 
                                                       uint64_t* cbuf, uint32_t ccap, const uint32_t* fbits, uint32_t ep,
                                                       int ef, int layer, Stats& st, bool& overflow) {
   const int lane = lane_id();
-  const float4* vec4 = reinterpret_cast<const float4*>(g.vec);
+  const uint4* vec4 = reinterpret_cast<const uint4*>(g.vec);
   vis.begin();
   if (lane == 0) s.cand_id[0] = ep;
   __syncwarp();
-  warp_dists<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, 1, s.cand_d);  // hnsw.rs:952
+  warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, 1, s.cand_d);  // hnsw.rs:952
   __syncwarp();
   st.evals += 1;
   const float d0 = s.cand_d[0];
@@ -105,7 +105,7 @@ __device__ __forceinline__ void search_layer_filtered(const GraphView& g, const 
         const int pos = __popc(m & ((1u << lane) - 1u));
         if (fresh) s.cand_id[pos] = nid;
         __syncwarp();
-        warp_dists<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, cnt, s.cand_d);  // 1026
+        warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, cnt, s.cand_d);  // 1026
         __syncwarp();
         st.evals += cnt;
         const uint32_t my_id = lane < cnt ? s.cand_id[lane] : 0u;
@@ -153,27 +153,24 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_filter_kernel(SearchPar
   unsigned char* base = smem_raw + (size_t)warp * p.smem_per_warp;
   const size_t stb = stage_bytes(g.d4);  // same per-warp layout as search.cu (the stage is unused here)
   WarpSmem s;
-  s.q4 = reinterpret_cast<float4*>(base + stb);
+  s.q4 = reinterpret_cast<uint4*>(base + stb);
   s.wbuf = reinterpret_cast<uint64_t*>(base + stb + (size_t)g.d4 * 16);
   s.cand_id = reinterpret_cast<uint32_t*>(base + stb + (size_t)g.d4 * 16 + (size_t)p.q_smem * 8);
   s.cand_d = reinterpret_cast<float*>(s.cand_id + 32);
-  float* qf = reinterpret_cast<float*>(s.q4);
   const uint32_t slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
   Visited vis;
   vis.init(p.vis, slot);
   uint64_t* cbuf = p.cbuf + (size_t)slot * p.ccap;
   SortedQueue W;
   Stats st{0, 0, 0};
-  const float4* vec4 = reinterpret_cast<const float4*>(g.vec);
+  const uint4* vec4 = reinterpret_cast<const uint4*>(g.vec);
 
   for (;;) {
     uint32_t qi = 0;
     if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= p.nq) break;
-    const float* qsrc = p.queries + (size_t)qi * p.q_stride;
-    for (int i = lane; i < g.d4 * 4; i += 32) qf[i] = i < p.d ? qsrc[i] : 0.f;
-    __syncwarp();
+    stage_row_bytes(s.q4, reinterpret_cast<const char*>(p.queries) + (size_t)qi * p.q_stride_bytes, p.q_bytes, g.d4 * 16);
     int count = 0;
     bool overflow = false;
     W.reset(s.wbuf, p.ef);
@@ -182,7 +179,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_filter_kernel(SearchPar
       uint32_t pivot = g.entry;
       if (lane == 0) s.cand_id[0] = pivot;
       __syncwarp();
-      warp_dists<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, 1, s.cand_d);
+      warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, 1, s.cand_d);
       __syncwarp();
       st.evals += 1;
       float best = s.cand_d[0];
@@ -198,7 +195,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_filter_kernel(SearchPar
             __syncwarp();
             if (lane < cnt) s.cand_id[lane] = nid;
             __syncwarp();
-            warp_dists<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, cnt, s.cand_d);
+            warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, cnt, s.cand_d);
             __syncwarp();
             st.evals += cnt;
             st.adj += cnt;
@@ -271,25 +268,19 @@ static cudaError_t launch_filter_for_op(const SearchParams& p, int grid, size_t 
     if (!query_only) kern<<<grid, SEARCH_THREADS, smem, st>>>(p);                                       \
     return cudaGetLastError();                                                                          \
   } while (0)
-  if (ch == 1) HB_LAUNCH(1, 4);
-  if (ch == 2) HB_LAUNCH(2, 4);
-  if (ch == 4) HB_LAUNCH(4, 2);
+  if constexpr (Specialise<Op>::value) {
+    if (ch == 4) HB_LAUNCH(4, 2);
+  }
   HB_LAUNCH(0, 2);
 #undef HB_LAUNCH
 }
 
-cudaError_t launch_search_filtered(const SearchParams& p, int metric, int grid, size_t smem, cudaStream_t st,
+cudaError_t launch_search_filtered(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
                                    bool query_only, int* blocks_per_sm) {
-  switch (metric) {
-    case METRIC_L1: return launch_filter_for_op<OpL1>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_L2: return launch_filter_for_op<OpL2>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_DOT: return launch_filter_for_op<OpDot>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_COSINE: return launch_filter_for_op<OpCosine>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_HELLINGER: return launch_filter_for_op<OpHellinger>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_JEFFREYS: return launch_filter_for_op<OpJeffreys>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_JENSENSHANNON: return launch_filter_for_op<OpJS>(p, grid, smem, st, query_only, blocks_per_sm);
-  }
-  return cudaErrorInvalidValue;
+  return dispatch_op(metric, dtype, [&](auto tag) -> cudaError_t {
+    using Op = typename decltype(tag)::type;
+    return launch_filter_for_op<Op>(p, grid, smem, st, query_only, blocks_per_sm);
+  });
 }
 
 }  // namespace hb

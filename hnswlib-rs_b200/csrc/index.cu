@@ -36,8 +36,9 @@ int Index::cuda_fail(cudaError_t e, const char* what) const {
   return -2;
 }
 
-Index::Index(int M_, size_t max_elements_, int max_layer_, int ef_c_, int metric_, int device_)
-    : M(M_), max_layer(std::min(max_layer_, MAX_LAYERS)), ef_c(ef_c_), metric(metric_), device(device_),
+Index::Index(int M_, size_t max_elements_, int max_layer_, int ef_c_, int metric_, int dtype_, int device_)
+    : M(M_), max_layer(std::min(max_layer_, MAX_LAYERS)), ef_c(ef_c_), metric(metric_), dtype(dtype_),
+      es(dtype_size(dtype_)), device(device_),
       max_elements(max_elements_) {
   for (int l = 0; l < MAX_LAYERS; ++l) layer_count[l] = 0;
   level_scale = 1.0 / std::log((double)M);  // hnsw.rs:327
@@ -103,7 +104,7 @@ int Index::set_dim(int d) {
   if (d <= 0) return fail("dimension must be positive");
   if (dim == 0) {
     dim = d;
-    d_pad = (d + 31) / 32 * 32;
+    row_bytes = (d * es + 127) / 128 * 128;
     return 0;
   }
   if (dim != d) return fail("vector length differs from the index dimension (the flat point store needs one dimension)");
@@ -117,7 +118,7 @@ int Index::ensure_points(size_t need) {
   if (cap_ == 0) nc = std::max(nc, std::max<size_t>(max_elements, 1024));
   const size_t deg0 = (size_t)2 * M;
   int r;
-  if ((r = grow(d_vec_, nc * d_pad, n * d_pad, 0))) return r;
+  if ((r = grow(d_vec_, nc * (size_t)row_bytes, n * (size_t)row_bytes, 0))) return r;
   if ((r = grow(d_adj0_, nc * deg0, n * deg0, 0xFF))) return r;
   if ((r = grow(d_adj0d_, nc * deg0, n * deg0, 0))) return r;
   if ((r = grow(d_upoff_, nc, n, 0xFF))) return r;
@@ -190,7 +191,8 @@ int Index::ensure_scratch(void** p, size_t* cur, size_t need) {
 GraphView Index::view() const {
   GraphView g;
   g.vec = d_vec_.p;
-  g.d4 = d_pad / 4;
+  g.d4 = row_bytes / 16;
+  g.dim = dim;
   g.adj0 = d_adj0_.p;
   g.adj0_d = d_adj0d_.p;
   g.deg0 = 2 * M;
@@ -259,7 +261,7 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
   const size_t smem = spw * (BUILD_THREADS / 32);
   if (smem > 220 * 1024) return fail("ef_construction / dimension too large for the insert kernel's shared memory");
   int bps = 0;
-  HB_CUDA(launch_insert_search(p, metric, 0, smem, stream_, true, &bps));
+  HB_CUDA(launch_insert_search(p, metric, dtype, 0, smem, stream_, true, &bps));
   if (bps < 1) return fail("insert kernel does not fit on an SM");
   const int wpb = BUILD_THREADS / 32;
   int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (count + wpb - 1) / wpb);
@@ -269,7 +271,7 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
     if ((r = ensure_visited((size_t)grid * wpb, vcap))) return r;
     if ((r = fill_visited_cfg(p.vis))) return r;
     HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
-    HB_CUDA(launch_insert_search(p, metric, grid, smem, stream_, false, nullptr));
+    HB_CUDA(launch_insert_search(p, metric, dtype, grid, smem, stream_, false, nullptr));
     int status = 0;
     HB_CUDA(cudaMemcpyAsync(&status, d_status_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
     HB_CUDA(cudaStreamSynchronize(stream_));
@@ -283,7 +285,7 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
   return 0;
 }
 
-int Index::insert_batch(const float* vecs, size_t n_new, size_t stride, const float* const* rows, const uint64_t* ids,
+int Index::insert_batch(const void* vecs, size_t n_new, size_t stride, const void* const* rows, const uint64_t* ids,
                         const int32_t* levels) {
   if (n_new == 0) return 0;
   if (dim == 0) return fail("dimension not set");
@@ -328,24 +330,25 @@ int Index::insert_batch(const float* vecs, size_t n_new, size_t stride, const fl
   }
   // ---- upload vectors (rows padded to d_pad on the device; the padding was zero-filled at allocation)
   if (rows) {
-    const size_t chunk = std::max<size_t>(1, (size_t)(8u << 20) / ((size_t)dim * 4));
-    if (h_pin_bytes_ < chunk * dim * 4) {
+    const size_t rb = (size_t)dim * es;  // bytes of one user row
+    const size_t chunk = std::max<size_t>(1, (size_t)(8u << 20) / rb);
+    if (h_pin_bytes_ < chunk * rb) {
       if (h_pin_) cudaFreeHost(h_pin_);
       h_pin_ = nullptr;
       h_pin_bytes_ = 0;
-      HB_CUDA(cudaMallocHost(&h_pin_, chunk * dim * 4));
-      h_pin_bytes_ = chunk * dim * 4;
+      HB_CUDA(cudaMallocHost(&h_pin_, chunk * rb));
+      h_pin_bytes_ = chunk * rb;
     }
     for (size_t b = 0; b < n_new; b += chunk) {
       const size_t c = std::min(chunk, n_new - b);
-      float* st = (float*)h_pin_;
-      for (size_t i = 0; i < c; ++i) memcpy(st + i * dim, rows[b + i], (size_t)dim * 4);
-      HB_CUDA(cudaMemcpy2DAsync(d_vec_.p + (first + b) * d_pad, (size_t)d_pad * 4, st, (size_t)dim * 4, (size_t)dim * 4, c,
+      unsigned char* st = (unsigned char*)h_pin_;
+      for (size_t i = 0; i < c; ++i) memcpy(st + i * rb, rows[b + i], rb);
+      HB_CUDA(cudaMemcpy2DAsync(d_vec_.p + (first + b) * (size_t)row_bytes, (size_t)row_bytes, st, rb, rb, c,
                                 cudaMemcpyHostToDevice, stream_));
       HB_CUDA(cudaStreamSynchronize(stream_));
     }
   } else {
-    HB_CUDA(cudaMemcpy2DAsync(d_vec_.p + first * d_pad, (size_t)d_pad * 4, vecs, stride * 4, (size_t)dim * 4, n_new,
+    HB_CUDA(cudaMemcpy2DAsync(d_vec_.p + first * (size_t)row_bytes, (size_t)row_bytes, vecs, stride * es, (size_t)dim * es, n_new,
                               cudaMemcpyHostToDevice, stream_));
   }
   HB_CUDA(cudaMemcpyAsync(d_level_.p + first, h_level.data() + first, n_new, cudaMemcpyHostToDevice, stream_));
@@ -394,7 +397,7 @@ int Index::insert_batch(const float* vecs, size_t n_new, size_t stride, const fl
 
 // ------------------------------------------------------------------------------------------------
 // import of a graph built elsewhere (oracle, another rank, a dump)
-int Index::import_graph(const float* vecs, size_t n_new, int d, const uint64_t* origin, const uint8_t* levels,
+int Index::import_graph(const void* vecs, size_t n_new, int d, const uint64_t* origin, const uint8_t* levels,
                         int64_t entry_id, int nlayers, const uint64_t* const* offsets, const uint32_t* const* ids,
                         const float* const* dists) {
   if (n != 0) return fail("import_graph needs an empty index");
@@ -469,7 +472,7 @@ int Index::import_graph(const float* vecs, size_t n_new, int d, const uint64_t* 
       }
     }
   }
-  HB_CUDA(cudaMemcpy2DAsync(d_vec_.p, (size_t)d_pad * 4, vecs, (size_t)dim * 4, (size_t)dim * 4, n_new, cudaMemcpyHostToDevice, stream_));
+  HB_CUDA(cudaMemcpy2DAsync(d_vec_.p, (size_t)row_bytes, vecs, (size_t)dim * es, (size_t)dim * es, n_new, cudaMemcpyHostToDevice, stream_));
   HB_CUDA(cudaMemcpyAsync(d_adj0_.p, a0.data(), a0.size() * 4, cudaMemcpyHostToDevice, stream_));
   HB_CUDA(cudaMemcpyAsync(d_adj0d_.p, a0d.data(), a0d.size() * 4, cudaMemcpyHostToDevice, stream_));
   if (n_ul) {
@@ -491,7 +494,7 @@ int Index::import_graph(const float* vecs, size_t n_new, int d, const uint64_t* 
 
 // ------------------------------------------------------------------------------------------------
 // search
-int Index::search_device(const float* d_queries, size_t nq, size_t k, size_t ef_arg, const uint32_t* d_filter_bits,
+int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_arg, const uint32_t* d_filter_bits,
                          NeighbourOut* d_out, int32_t* d_counts, bool sync, float* kernel_ms) {
   if (nq == 0) return 0;
   if (k == 0) return fail("knbn must be positive");
@@ -504,8 +507,8 @@ int Index::search_device(const float* d_queries, size_t nq, size_t k, size_t ef_
   SearchParams p;
   p.g = view();
   p.queries = d_queries;
-  p.d = dim;
-  p.q_stride = dim;
+  p.q_bytes = dim * es;
+  p.q_stride_bytes = dim * es;
   p.nq = (uint32_t)nq;
   p.k = (int)k;
   p.ef = (int)std::max(ef_arg, k);  // hnsw.rs:1531
@@ -529,8 +532,8 @@ int Index::search_device(const float* d_queries, size_t nq, size_t k, size_t ef_
   p.cbuf = nullptr;
   p.ccap = 0;
   int bps = 0;
-  if (filtered) HB_CUDA(launch_search_filtered(p, metric, 0, smem, stream_, true, &bps));
-  else HB_CUDA(launch_search(p, metric, 0, smem, stream_, true, &bps));
+  if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, 0, smem, stream_, true, &bps));
+  else HB_CUDA(launch_search(p, metric, dtype, 0, smem, stream_, true, &bps));
   if (bps < 1) return fail("search kernel does not fit on an SM");
   int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (nq + wpb - 1) / wpb);
   const int deg = layer0 == 0 ? 2 * M : M;
@@ -553,8 +556,8 @@ int Index::search_device(const float* d_queries, size_t nq, size_t k, size_t ef_
     }
     HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
     HB_CUDA(cudaEventRecord(ev0_, stream_));
-    if (filtered) HB_CUDA(launch_search_filtered(p, metric, grid, smem, stream_, false, nullptr));
-    else HB_CUDA(launch_search(p, metric, grid, smem, stream_, false, nullptr));
+    if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, grid, smem, stream_, false, nullptr));
+    else HB_CUDA(launch_search(p, metric, dtype, grid, smem, stream_, false, nullptr));
     HB_CUDA(cudaEventRecord(ev1_, stream_));
     if (!sync) break;
     int status = 0;
@@ -572,7 +575,7 @@ int Index::search_device(const float* d_queries, size_t nq, size_t k, size_t ef_
   return 0;
 }
 
-int Index::search_host(const float* queries, const float* const* rows, size_t nq, int d, size_t k, size_t ef,
+int Index::search_host(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
                        const uint32_t* filter_bits_host, NeighbourOut* out, int32_t* counts) {
   if (nq == 0) return 0;
   HB_CUDA(cudaSetDevice(device));
@@ -582,7 +585,7 @@ int Index::search_host(const float* queries, const float* const* rows, size_t nq
     return 0;
   }
   int r;
-  const size_t qbytes = nq * (size_t)dim * 4;
+  const size_t qbytes = nq * (size_t)dim * es;
   if ((r = ensure_scratch(&d_q_, &d_q_bytes_, qbytes))) return r;
   if ((r = ensure_scratch(&d_out_, &d_out_bytes_, nq * k * sizeof(NeighbourOut)))) return r;
   if ((r = ensure_scratch(&d_cnt_, &d_cnt_bytes_, nq * sizeof(int32_t)))) return r;
@@ -594,8 +597,8 @@ int Index::search_host(const float* queries, const float* const* rows, size_t nq
       HB_CUDA(cudaMallocHost(&h_pin_, qbytes));
       h_pin_bytes_ = qbytes;
     }
-    float* st = (float*)h_pin_;
-    for (size_t i = 0; i < nq; ++i) memcpy(st + i * dim, rows[i], (size_t)dim * 4);
+    unsigned char* st = (unsigned char*)h_pin_;
+    for (size_t i = 0; i < nq; ++i) memcpy(st + i * (size_t)dim * es, rows[i], (size_t)dim * es);
     HB_CUDA(cudaMemcpyAsync(d_q_, st, qbytes, cudaMemcpyHostToDevice, stream_));
   } else {
     HB_CUDA(cudaMemcpyAsync(d_q_, queries, qbytes, cudaMemcpyHostToDevice, stream_));
@@ -607,7 +610,7 @@ int Index::search_host(const float* queries, const float* const* rows, size_t nq
     HB_CUDA(cudaMemcpyAsync(d_fbits_, filter_bits_host, fb, cudaMemcpyHostToDevice, stream_));
     dfb = (const uint32_t*)d_fbits_;
   }
-  if ((r = search_device((const float*)d_q_, nq, k, ef, dfb, (NeighbourOut*)d_out_, (int32_t*)d_cnt_, true, nullptr))) return r;
+  if ((r = search_device(d_q_, nq, k, ef, dfb, (NeighbourOut*)d_out_, (int32_t*)d_cnt_, true, nullptr))) return r;
   HB_CUDA(cudaMemcpyAsync(out, d_out_, nq * k * sizeof(NeighbourOut), cudaMemcpyDeviceToHost, stream_));
   HB_CUDA(cudaMemcpyAsync(counts, d_cnt_, nq * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
   HB_CUDA(cudaStreamSynchronize(stream_));
@@ -680,10 +683,10 @@ int Index::export_layer(int layer, uint64_t* offsets, uint32_t* ids, float* dist
   return 0;
 }
 
-int Index::export_vectors(float* out) const {
+int Index::export_vectors(void* out) const {
   if (n == 0) return 0;
   cudaSetDevice(device);
-  HB_CUDA(cudaMemcpy2D(out, (size_t)dim * 4, d_vec_.p, (size_t)d_pad * 4, (size_t)dim * 4, n, cudaMemcpyDeviceToHost));
+  HB_CUDA(cudaMemcpy2D(out, (size_t)dim * es, d_vec_.p, (size_t)row_bytes, (size_t)dim * es, n, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -741,13 +744,15 @@ int Index::blob_header(uint64_t* h) const {
   h[8] = entry;
   h[9] = (uint64_t)(int64_t)entry_level;
   h[10] = 1;  // distances included
+  h[11] = (uint64_t)dtype;
   return 0;
 }
 
 int Index::blob_alloc(const uint64_t* h) {
   if (h[0] != BLOB_MAGIC) return fail("bad replication header");
   if (n != 0) return fail("blob_alloc needs an empty index");
-  if ((int)h[3] != M || (int)h[6] != metric) return fail("replication header does not match this handle's M / metric");
+  if ((int)h[3] != M || (int)h[6] != metric || (int)h[11] != dtype)
+    return fail("replication header does not match this handle's M / metric / element type");
   HB_CUDA(cudaSetDevice(device));
   int r;
   if ((r = set_dim((int)h[2]))) return r;
@@ -765,7 +770,7 @@ int Index::blob_alloc(const uint64_t* h) {
 int Index::blob_info(int i, void** p, uint64_t* bytes) const {
   const size_t deg0 = (size_t)2 * M;
   switch (i) {
-    case 0: *p = d_vec_.p; *bytes = n * d_pad * 4; return 0;
+    case 0: *p = d_vec_.p; *bytes = n * (size_t)row_bytes; return 0;
     case 1: *p = d_adj0_.p; *bytes = n * deg0 * 4; return 0;
     case 2: *p = d_adjU_.p; *bytes = n_ul * M * 4; return 0;
     case 3: *p = d_upoff_.p; *bytes = n * 4; return 0;

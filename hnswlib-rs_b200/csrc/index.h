@@ -34,12 +34,12 @@ struct DevArray {  // growable device array, contents preserved on growth
 
 class Index {
  public:
-  Index(int M, size_t max_elements, int max_layer, int ef_c, int metric, int device);
+  Index(int M, size_t max_elements, int max_layer, int ef_c, int metric, int dtype, int device);
   ~Index();
   bool ok() const { return ok_; }
 
   // ---- configuration (Hnsw::new and setters, hnsw.rs:771-905)
-  int M, max_layer, ef_c, metric, device;
+  int M, max_layer, ef_c, metric, dtype, es, device;  // es = bytes per element
   size_t max_elements;
   bool extend_candidates = false, keep_pruned = false, searching = false;
   double level_scale;  // 1/ln(M) * factor
@@ -47,7 +47,7 @@ class Index {
   uint32_t batch_ratio = 16, batch_max = 16384;
 
   // ---- state
-  int dim = 0, d_pad = 0;
+  int dim = 0, row_bytes = 0;  // row_bytes = dim*es rounded up to whole 128-byte lines
   size_t n = 0;          // points stored (all linked: inserts are synchronous per call)
   size_t n_ul = 0;       // upper lists allocated
   size_t layer_count[MAX_LAYERS];
@@ -61,22 +61,22 @@ class Index {
   // ---- operations (return 0 or a negative status; message in err())
   int set_dim(int d);
   int draw_level();
-  int insert_batch(const float* vecs, size_t n_new, size_t stride, const float* const* rows, const uint64_t* ids,
+  int insert_batch(const void* vecs, size_t n_new, size_t stride, const void* const* rows, const uint64_t* ids,
                    const int32_t* levels);
-  int import_graph(const float* vecs, size_t n_new, int d, const uint64_t* origin, const uint8_t* levels,
+  int import_graph(const void* vecs, size_t n_new, int d, const uint64_t* origin, const uint8_t* levels,
                    int64_t entry_id, int nlayers, const uint64_t* const* offsets, const uint32_t* const* ids,
                    const float* const* dists);
   // host queries (flat or row pointers); results to host NeighbourOut[nq][k] + counts
-  int search_host(const float* queries, const float* const* rows, size_t nq, int d, size_t k, size_t ef,
+  int search_host(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
                   const uint32_t* filter_bits_host, NeighbourOut* out, int32_t* counts);
-  int search_device(const float* d_queries, size_t nq, size_t k, size_t ef, const uint32_t* d_filter_bits,
+  int search_device(const void* d_queries, size_t nq, size_t k, size_t ef, const uint32_t* d_filter_bits,
                     NeighbourOut* d_out, int32_t* d_counts, bool sync, float* kernel_ms);
   // filter materialisation: bit per internal id from a sorted origin-id list or a callback
   int make_filter_bits(int mode, const uint64_t* sorted_ids, size_t nids, int (*fn)(uint64_t, void*), void* ctx,
                        std::vector<uint32_t>& bits) const;
 
   int export_layer(int layer, uint64_t* offsets, uint32_t* ids, float* dists, int64_t* total) const;
-  int export_vectors(float* out) const;
+  int export_vectors(void* out) const;
   int enable_stats(bool on);
   int get_stats(uint64_t* out4, bool reset);
 
@@ -87,8 +87,8 @@ class Index {
   int blob_info(int i, void** p, uint64_t* bytes) const;
   int blob_commit();
 
-  int dist_batch(const float* queries, size_t nq, int d, const uint32_t* cand, size_t m, float* out);
-  int bruteforce(const float* queries, size_t nq, int d, size_t k, uint32_t* out_ids, float* out_dist);
+  int dist_batch(const void* queries, size_t nq, int d, const uint32_t* cand, size_t m, float* out);
+  int bruteforce(const void* queries, size_t nq, int d, size_t k, uint32_t* out_ids, float* out_dist);
 
   const std::string& err() const { return err_; }
   GraphView view() const;
@@ -116,7 +116,7 @@ class Index {
   int sm_count_ = 0;
 
   size_t cap_ = 0, cap_ul_ = 0;
-  DevArray<float> d_vec_;
+  DevArray<unsigned char> d_vec_;
   DevArray<uint32_t> d_adj0_, d_adjU_, d_upoff_;
   DevArray<float> d_adj0d_, d_adjUd_;
   DevArray<uint8_t> d_level_, d_plevel_;

@@ -8,6 +8,9 @@
 
 namespace hb {
 
+enum DType : int { DT_F32 = 0, DT_U8 = 1, DT_U16 = 2, DT_U32 = 3, DT_I32 = 4 };
+inline int dtype_size(int dt) { return dt == DT_U8 ? 1 : dt == DT_U16 ? 2 : 4; }
+
 constexpr int SEARCH_THREADS = 256;  // 8 warps = 8 queries in flight per CTA
 constexpr int BUILD_THREADS = 128;   // 4 warps = 4 inserts in flight per CTA
 
@@ -21,9 +24,9 @@ struct NeighbourOut {
 
 struct SearchParams {
   GraphView g;
-  const float* queries;  // device, [nq][q_stride]
-  int d;
-  int q_stride;
+  const void* queries;  // device, raw element bytes, row i at i * q_stride_bytes
+  int q_bytes;          // bytes of one query = dim * sizeof(T)
+  int q_stride_bytes;
   uint32_t nq;
   int k;
   int ef;      // already max(ef_arg, k), hnsw.rs:1531
@@ -82,13 +85,72 @@ inline size_t insert_smem_per_warp(int d4, int ef_c, int deg0, int q_smem) {
   return (b + 127) & ~(size_t)127;
 }
 
-cudaError_t launch_insert_search(const InsertParams& p, int metric, int grid, size_t smem, cudaStream_t st,
+cudaError_t launch_insert_search(const InsertParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
                                  bool query_only, int* blocks_per_sm);
 cudaError_t launch_insert_link(const InsertParams& p, int grid, cudaStream_t st);
 
-cudaError_t launch_search_filtered(const SearchParams& p, int metric, int grid, size_t smem, cudaStream_t st,
+cudaError_t launch_search_filtered(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
                                    bool query_only, int* blocks_per_sm);
-cudaError_t launch_search(const SearchParams& p, int metric, int grid, size_t smem, cudaStream_t st, bool query_only,
+cudaError_t launch_search(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st, bool query_only,
                           int* blocks_per_sm);
+
+// ---- (metric, element type) -> distance functor.  f is called as f(OpTag<Op>{}) and returns cudaError_t.
+template <class Op>
+struct OpTag {
+  typedef Op type;
+};
+// CH-specialised kernels (compile-time row length) are only built for the common f32 metrics
+template <class Op>
+struct Specialise {
+  static constexpr bool value = false;
+};
+template <> struct Specialise<OpL1> { static constexpr bool value = true; };
+template <> struct Specialise<OpL2> { static constexpr bool value = true; };
+template <> struct Specialise<OpDot> { static constexpr bool value = true; };
+template <> struct Specialise<OpCosine> { static constexpr bool value = true; };
+
+template <class T, class F>
+cudaError_t dispatch_int(int metric, bool with_jaccard, F&& f) {
+  switch (metric) {
+    case METRIC_L1: return f(OpTag<OpCast<T, OpL1>>{});
+    case METRIC_L2: return f(OpTag<OpCast<T, OpL2>>{});
+    case METRIC_HAMMING: return f(OpTag<OpHamming<T>>{});
+    case METRIC_JACCARD:
+      if (with_jaccard) return f(OpTag<OpJaccard<T>>{});
+      break;
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <class F>
+cudaError_t dispatch_op(int metric, int dtype, F&& f) {
+  switch (dtype) {
+    case DT_F32:
+      switch (metric) {
+        case METRIC_L1: return f(OpTag<OpL1>{});
+        case METRIC_L2: return f(OpTag<OpL2>{});
+        case METRIC_DOT: return f(OpTag<OpDot>{});
+        case METRIC_COSINE: return f(OpTag<OpCosine>{});
+        case METRIC_HELLINGER: return f(OpTag<OpHellinger>{});
+        case METRIC_JEFFREYS: return f(OpTag<OpJeffreys>{});
+        case METRIC_JENSENSHANNON: return f(OpTag<OpJS>{});
+      }
+      break;
+    case DT_U8: return dispatch_int<uint8_t>(metric, true, f);
+    case DT_U16: return dispatch_int<uint16_t>(metric, true, f);
+    case DT_U32: return dispatch_int<uint32_t>(metric, true, f);
+    case DT_I32: return dispatch_int<int32_t>(metric, false, f);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// which (metric, dtype) pairs exist (mirrors init_hnsw_{f32,i32,u32,u16,u8} in /root/reference/src/libext.rs)
+inline bool metric_supported(int metric, int dtype) {
+  if (dtype == DT_F32)
+    return metric == METRIC_L1 || metric == METRIC_L2 || metric == METRIC_DOT || metric == METRIC_COSINE ||
+           metric == METRIC_HELLINGER || metric == METRIC_JEFFREYS || metric == METRIC_JENSENSHANNON;
+  if (metric == METRIC_L1 || metric == METRIC_L2 || metric == METRIC_HAMMING) return true;
+  return metric == METRIC_JACCARD && dtype != DT_I32;
+}
 
 }  // namespace hb

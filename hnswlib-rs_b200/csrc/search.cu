@@ -17,13 +17,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
   // per-warp layout: [TMA stage][query][queue keys][cand ids][cand dists][mbarrier]
   const size_t stb = stage_bytes(g.d4);
   WarpSmem s;
-  s.q4 = reinterpret_cast<float4*>(base + stb);
+  s.q4 = reinterpret_cast<uint4*>(base + stb);
   s.wbuf = reinterpret_cast<uint64_t*>(base + stb + (size_t)g.d4 * 16);
   s.cand_id = reinterpret_cast<uint32_t*>(base + stb + (size_t)g.d4 * 16 + (size_t)p.q_smem * 8);
   s.cand_d = reinterpret_cast<float*>(s.cand_id + 32);
-  float* qf = reinterpret_cast<float*>(s.q4);
   Stage stg;
-  stg.buf = stb ? reinterpret_cast<float4*>(base) : nullptr;
+  stg.buf = stb ? reinterpret_cast<uint4*>(base) : nullptr;
   stg.bar = reinterpret_cast<uint64_t*>(s.cand_d + 32);
   stg.phase = 0;
   if (lane == 0) mbar_init(stg.bar, 1);
@@ -35,7 +34,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
   Queue Q;
   Q.reset(s.wbuf, p.ef);
   Stats st{0, 0, 0};
-  const float4* vec4 = reinterpret_cast<const float4*>(g.vec);
+  const uint4* vec4 = reinterpret_cast<const uint4*>(g.vec);
 
   for (;;) {
     uint32_t qi = 0;
@@ -43,9 +42,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= p.nq) break;
     // stage the query (zero padded to d_pad)
-    const float* qsrc = p.queries + (size_t)qi * p.q_stride;
-    for (int i = lane; i < g.d4 * 4; i += 32) qf[i] = i < p.d ? qsrc[i] : 0.f;
-    __syncwarp();
+    stage_row_bytes(s.q4, reinterpret_cast<const char*>(p.queries) + (size_t)qi * p.q_stride_bytes, p.q_bytes, g.d4 * 16);
 
     int count = 0;
     bool overflow = false;
@@ -54,7 +51,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
       uint32_t pivot = g.entry;
       if (lane == 0) s.cand_id[0] = pivot;
       __syncwarp();
-      warp_dists<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, 1, s.cand_d);  // hnsw.rs:1506
+      warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, 1, s.cand_d);  // hnsw.rs:1506
       __syncwarp();
       st.evals += 1;
       float best = s.cand_d[0];
@@ -70,7 +67,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
             __syncwarp();
             if (lane < cnt) s.cand_id[lane] = nid;
             __syncwarp();
-            warp_dists<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, cnt, s.cand_d);  // hnsw.rs:1518
+            warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, cnt, s.cand_d);  // hnsw.rs:1518
             __syncwarp();
             st.evals += cnt;
             st.adj += cnt;
@@ -139,34 +136,26 @@ static cudaError_t launch_for_op(const SearchParams& p, int grid, size_t smem, c
     if (!query_only) kern<<<grid, SEARCH_THREADS, smem, st>>>(p);                                               \
     return cudaGetLastError();                                                                                  \
   } while (0)
-  if (ch == 1) HB_LAUNCH(1, 4);
-  if (ch == 2) HB_LAUNCH(2, 4);
-  if (ch == 4) HB_LAUNCH(4, 2);
+  if constexpr (Specialise<Op>::value) {
+    if (ch == 1) HB_LAUNCH(1, 4);
+    if (ch == 2) HB_LAUNCH(2, 4);
+    if (ch == 4) HB_LAUNCH(4, 2);
+  }
   HB_LAUNCH(0, 2);
 #undef HB_LAUNCH
 }
 
-template <class Op>
-static cudaError_t launch_common(const SearchParams& p, int grid, size_t smem, cudaStream_t st, bool query_only,
-                                 int* blocks_per_sm) {
-  const int ns = p.q_smem ? 0 : queue_stripes(p.ef, METRIC_L2);
-  if (ns == 2) return launch_for_op<Op, 2>(p, grid, smem, st, query_only, blocks_per_sm);
-  if (ns == 8) return launch_for_op<Op, 8>(p, grid, smem, st, query_only, blocks_per_sm);
-  return launch_for_op<Op, 0>(p, grid, smem, st, query_only, blocks_per_sm);
-}
-
-cudaError_t launch_search(const SearchParams& p, int metric, int grid, size_t smem, cudaStream_t st, bool query_only,
-                          int* blocks_per_sm) {
-  switch (metric) {
-    case METRIC_L1: return launch_common<OpL1>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_L2: return launch_common<OpL2>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_DOT: return launch_common<OpDot>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_COSINE: return launch_common<OpCosine>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_HELLINGER: return launch_for_op<OpHellinger, 0>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_JEFFREYS: return launch_for_op<OpJeffreys, 0>(p, grid, smem, st, query_only, blocks_per_sm);
-    case METRIC_JENSENSHANNON: return launch_for_op<OpJS, 0>(p, grid, smem, st, query_only, blocks_per_sm);
-  }
-  return cudaErrorInvalidValue;
+cudaError_t launch_search(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
+                          bool query_only, int* blocks_per_sm) {
+  return dispatch_op(metric, dtype, [&](auto tag) -> cudaError_t {
+    using Op = typename decltype(tag)::type;
+    if constexpr (Specialise<Op>::value) {
+      const int ns = p.q_smem ? 0 : queue_stripes(p.ef, METRIC_L2);
+      if (ns == 2) return launch_for_op<Op, 2>(p, grid, smem, st, query_only, blocks_per_sm);
+      if (ns == 8) return launch_for_op<Op, 8>(p, grid, smem, st, query_only, blocks_per_sm);
+    }
+    return launch_for_op<Op, 0>(p, grid, smem, st, query_only, blocks_per_sm);
+  });
 }
 
 }  // namespace hb

@@ -7,7 +7,7 @@
 namespace hb {
 
 struct WarpSmem {
-  float4* q4;         // query, d4 float4 (zero padded)
+  uint4* q4;          // query row, d4 16-byte chunks (zero padded)
   uint64_t* wbuf;     // queue keys, capacity >= ef
   uint32_t* cand_id;  // 32
   float* cand_d;      // 32
@@ -28,11 +28,11 @@ template <class Op, int CH, int U, class Queue>
 __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem& s, Stage& stg, Visited& vis,
                                              Queue& Q, uint32_t ep, int ef, int layer, Stats& st, bool& overflow) {
   const int lane = lane_id();
-  const float4* vec4 = reinterpret_cast<const float4*>(g.vec);
+  const uint4* vec4 = reinterpret_cast<const uint4*>(g.vec);
   vis.begin();
   if (lane == 0) s.cand_id[0] = ep;
   __syncwarp();
-  warp_dists<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, 1, s.cand_d);  // hnsw.rs:952
+  warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, 1, s.cand_d);  // hnsw.rs:952
   __syncwarp();
   st.evals += 1;
   const float d0 = s.cand_d[0];
@@ -70,7 +70,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
         const int pos = __popc(m & ((1u << lane) - 1u));
         if (fresh) s.cand_id[pos] = nid;
         __syncwarp();
-        warp_dists_staged<Op, CH, U>(vec4, g.d4, s.q4, s.cand_id, cnt, s.cand_d, stg);  // hnsw.rs:1026
+        warp_dists_staged<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, cnt, s.cand_d, stg);  // hnsw.rs:1026
         __syncwarp();
         st.evals += cnt;
         const uint64_t key = lane < cnt ? make_key(s.cand_d[lane], s.cand_id[lane]) : ~0ull;

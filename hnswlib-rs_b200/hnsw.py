@@ -43,21 +43,20 @@ def load_library():
         raise RuntimeError(f"{_LIB_PATH} is missing: run __graft_entry__.build() (make -C hnswlib-rs_b200/csrc)")
     L = C.CDLL(_LIB_PATH)
     vp, u64, sz, i32, i64 = C.c_void_p, C.c_uint64, C.c_size_t, C.c_int, C.c_int64
-    L.init_hnsw_f32.restype = vp
-    L.init_hnsw_f32.argtypes = [sz, sz, sz, C.c_char_p]
-    L.new_hnsw_f32.restype = vp
-    L.new_hnsw_f32.argtypes = [sz, sz, sz, C.c_char_p, sz, sz]
-    L.drop_hnsw_f32.argtypes = [vp]
-    L.init_hnsw_ptrdist_f32.restype = vp
-    L.init_hnsw_ptrdist_f32.argtypes = [sz, sz, vp]
-    L.insert_f32.argtypes = [vp, sz, vp, sz]
-    L.parallel_insert_f32.argtypes = [vp, sz, sz, vp, vp]
-    L.search_neighbours_f32.restype = C.POINTER(Neighbourhood_api)
-    L.search_neighbours_f32.argtypes = [vp, sz, vp, sz, sz]
-    L.parallel_search_neighbours_f32.restype = C.POINTER(Vec_api)
-    L.parallel_search_neighbours_f32.argtypes = [vp, sz, i64, vp, sz, sz]
-    L.file_dump_f32.restype = i64
-    L.file_dump_f32.argtypes = [vp, sz, C.c_char_p]
+    for suf in ("f32", "i32", "u32", "u16", "u8"):   # libext.rs generates one set per element type
+        f = getattr(L, "init_hnsw_" + suf); f.restype = vp; f.argtypes = [sz, sz, sz, C.c_char_p]
+        f = getattr(L, "init_hnsw_ptrdist_" + suf); f.restype = vp; f.argtypes = [sz, sz, vp]
+        getattr(L, "insert_" + suf).argtypes = [vp, sz, vp, sz]
+        getattr(L, "parallel_insert_" + suf).argtypes = [vp, sz, sz, vp, vp]
+        f = getattr(L, "search_neighbours_" + suf); f.restype = C.POINTER(Neighbourhood_api); f.argtypes = [vp, sz, vp, sz, sz]
+        f = getattr(L, "parallel_search_neighbours_" + suf); f.restype = C.POINTER(Vec_api); f.argtypes = [vp, sz, i64, vp, sz, sz]
+        f = getattr(L, "file_dump_" + suf); f.restype = i64; f.argtypes = [vp, sz, C.c_char_p]
+    for suf in ("f32", "u16"):
+        f = getattr(L, "new_hnsw_" + suf); f.restype = vp; f.argtypes = [sz, sz, sz, C.c_char_p, sz, sz]
+        getattr(L, "drop_hnsw_" + suf).argtypes = [vp]
+    L.hnsw_b200_new.restype = vp
+    L.hnsw_b200_new.argtypes = [i32, sz, sz, sz, C.c_char_p, sz, sz]
+    L.hnsw_b200_drop.argtypes = [vp]
     L.hnsw_b200_last_error.restype = C.c_char_p
     L.hnsw_b200_device_count.restype = i32
     L.hnsw_b200_set_device.argtypes = [i32]
@@ -124,20 +123,32 @@ class Neighbour:
         return f"Neighbour(d_id={self.d_id}, distance={self.distance!r}, p_id={self.p_id})"
 
 
-class Hnsw:
-    """Hnsw<f32, D>: D given by name ("DistL2", "DistDot", "DistCosine", "DistL1", ...)."""
+_DT = {np.dtype(np.float32): (0, "f32"), np.dtype(np.uint8): (1, "u8"), np.dtype(np.uint16): (2, "u16"),
+       np.dtype(np.uint32): (3, "u32"), np.dtype(np.int32): (4, "i32")}
 
-    def __init__(self, max_nb_connection, max_elements, max_layer, ef_construction, dist_name, device=None):
+
+class Hnsw:
+    """Hnsw<T, D>: T = dtype (f32 default; i32/u32/u16/u8), D given by name ("DistL2", "DistDot", "DistCosine",
+    "DistL1", "DistHamming", "DistJaccard", ...)."""
+
+    def __init__(self, max_nb_connection, max_elements, max_layer, ef_construction, dist_name, device=None,
+                 dtype=np.float32):
         L = load_library()
         if device is not None:
             if L.hnsw_b200_set_device(int(device)) != 0:
                 raise HnswError(last_error())
         name = dist_name.encode()
         self._L = L
-        self._h = L.new_hnsw_f32(int(max_nb_connection), int(ef_construction), len(name), name, int(max_elements),
-                                 int(max_layer))
+        self.dtype = np.dtype(dtype)
+        code, self._suf = _DT[self.dtype]
+        if self._suf in ("f32", "u16"):   # the reference's own constructor with max_elements / max_layer
+            ctor = getattr(L, "new_hnsw_" + self._suf)
+            self._h = ctor(int(max_nb_connection), int(ef_construction), len(name), name, int(max_elements), int(max_layer))
+        else:
+            self._h = L.hnsw_b200_new(code, int(max_nb_connection), int(ef_construction), len(name), name,
+                                      int(max_elements), int(max_layer))
         if not self._h:
-            raise HnswError("new_hnsw_f32 failed: " + last_error())
+            raise HnswError("new_hnsw failed: " + last_error())
         self.dist_name = dist_name
         self.max_nb_connection = int(max_nb_connection)
         self.ef_construction = int(ef_construction)
@@ -145,7 +156,7 @@ class Hnsw:
     # ---- lifetime
     def close(self):
         if getattr(self, "_h", None):
-            self._L.drop_hnsw_f32(self._h)
+            self._L.hnsw_b200_drop(self._h)
             self._h = None
 
     def __del__(self):
@@ -195,9 +206,9 @@ class Hnsw:
     # ---- insertion (hnsw.rs:1069-1071, 1224-1238; api.rs:47-56)
     def insert(self, data_with_id):
         v, i = data_with_id
-        v = np.ascontiguousarray(v, np.float32)
+        v = np.ascontiguousarray(v, self.dtype)
         before = self.get_nb_point()
-        self._L.insert_f32(self._h, v.size, _p(v), int(i))
+        getattr(self._L, "insert_" + self._suf)(self._h, v.size, _p(v), int(i))
         if self.get_nb_point() != before + 1:
             raise HnswError("insert_f32 failed: " + last_error())
 
@@ -207,12 +218,12 @@ class Hnsw:
         """datas: sequence of (vector, id) — goes through parallel_insert_f32 (row pointers)."""
         if len(datas) == 0:
             return
-        rows = [np.ascontiguousarray(v, np.float32) for v, _ in datas]
+        rows = [np.ascontiguousarray(v, self.dtype) for v, _ in datas]
         d = rows[0].size
         ptrs = (C.c_void_p * len(rows))(*[r.ctypes.data for r in rows])
         ids = (C.c_size_t * len(rows))(*[int(i) for _, i in datas])
         before = self.get_nb_point()
-        self._L.parallel_insert_f32(self._h, len(rows), d, ptrs, ids)
+        getattr(self._L, "parallel_insert_" + self._suf)(self._h, len(rows), d, ptrs, ids)
         if self.get_nb_point() != before + len(rows):
             raise HnswError("parallel_insert_f32 failed: " + last_error())
 
@@ -221,7 +232,7 @@ class Hnsw:
 
     def insert_flat(self, vecs, ids=None, levels=None):
         """Extension: one flat [n, d] array (no per-row pointers)."""
-        vecs = np.ascontiguousarray(vecs, np.float32)
+        vecs = np.ascontiguousarray(vecs, self.dtype)
         n, d = vecs.shape
         ids_a = None if ids is None else np.ascontiguousarray(ids, np.uint64)
         lv = None if levels is None else np.ascontiguousarray(levels, np.int32)
@@ -239,8 +250,8 @@ class Hnsw:
     def search_filter(self, data, knbn, ef_arg, filter=None):
         """filter: None | sorted sequence of ids (FilterT for Vec<usize>) | callable(id)->bool."""
         if filter is None:
-            v = np.ascontiguousarray(data, np.float32)
-            res = self._L.search_neighbours_f32(self._h, v.size, _p(v), int(knbn), int(ef_arg))
+            v = np.ascontiguousarray(data, self.dtype)
+            res = getattr(self._L, "search_neighbours_" + self._suf)(self._h, v.size, _p(v), int(knbn), int(ef_arg))
             if not res:
                 raise HnswError("search_neighbours_f32 failed: " + last_error())
             n = res.contents.nbgh
@@ -249,16 +260,16 @@ class Hnsw:
             self._L.hnsw_b200_free_neighbourhood(res)
             # p_id needs the extension call; fetch lazily through search_flat when asked for
             return [Neighbour(i, d, None) for i, d in zip(ids, ds)]
-        o, d, it, pid, cnt = self.search_flat(np.asarray(data, np.float32)[None, :], knbn, ef_arg, filter=filter)
+        o, d, it, pid, cnt = self.search_flat(np.asarray(data, self.dtype)[None, :], knbn, ef_arg, filter=filter)
         return [Neighbour(int(o[0, j]), float(d[0, j]), (int(pid[0, j, 0]), int(pid[0, j, 1]))) for j in range(cnt[0])]
 
     def parallel_search(self, datas, knbn, ef):
         """Vec<Vec<Neighbour>> in input order, through parallel_search_neighbours_f32 (row pointers)."""
-        rows = [np.ascontiguousarray(v, np.float32) for v in datas]
+        rows = [np.ascontiguousarray(v, self.dtype) for v in datas]
         if not rows:
             return []
         ptrs = (C.c_void_p * len(rows))(*[r.ctypes.data for r in rows])
-        res = self._L.parallel_search_neighbours_f32(self._h, len(rows), rows[0].size, ptrs, int(knbn), int(ef))
+        res = getattr(self._L, "parallel_search_neighbours_" + self._suf)(self._h, len(rows), rows[0].size, ptrs, int(knbn), int(ef))
         if not res:
             raise HnswError("parallel_search_neighbours_f32 failed: " + last_error())
         out = []
@@ -272,7 +283,7 @@ class Hnsw:
 
     def search_flat(self, queries, knbn, ef, filter=None):
         """Extension: flat batch.  Returns (origin u64[nq,k], dist f32[nq,k], internal u32[nq,k], pid i32[nq,k,2], counts)."""
-        q = np.ascontiguousarray(queries, np.float32)
+        q = np.ascontiguousarray(queries, self.dtype)
         nq, d = q.shape
         o = np.empty((nq, knbn), np.uint64)
         ds = np.empty((nq, knbn), np.float32)
@@ -294,7 +305,7 @@ class Hnsw:
 
     def file_dump(self, path, basename):
         name = basename.encode()
-        r = self._L.file_dump_f32(self._h, len(name), name)
+        r = getattr(self._L, "file_dump_" + self._suf)(self._h, len(name), name)
         if r != 1:
             raise HnswError("file_dump_f32 failed: " + last_error())
         return basename
@@ -355,7 +366,7 @@ class Hnsw:
         return lv, rk, og, int(e.value)
 
     def export_vectors(self):
-        out = np.empty((self.get_nb_point(), self.get_data_dimension()), np.float32)
+        out = np.empty((self.get_nb_point(), self.get_data_dimension()), self.dtype)
         self._chk(self._L.hnsw_b200_export_vectors(self._h, _p(out)))
         return out
 
@@ -370,7 +381,7 @@ class Hnsw:
 
     def import_graph(self, vecs, origin, levels, entry, layers):
         """layers: list (index = layer) of (offsets u64[N+1], ids u32[], dists f32[]|None)."""
-        vecs = np.ascontiguousarray(vecs, np.float32)
+        vecs = np.ascontiguousarray(vecs, self.dtype)
         n, d = vecs.shape
         origin = np.ascontiguousarray(origin, np.uint64)
         levels = np.ascontiguousarray(levels, np.uint8)
@@ -388,14 +399,14 @@ class Hnsw:
                                                  idss, dss))
 
     def dist_batch(self, queries, cand):
-        q = np.ascontiguousarray(queries, np.float32)
+        q = np.ascontiguousarray(queries, self.dtype)
         c = np.ascontiguousarray(cand, np.uint32)
         out = np.empty(c.shape, np.float32)
         self._chk(self._L.hnsw_b200_dist_batch(self._h, _p(q), q.shape[0], q.shape[1], _p(c), c.shape[1], _p(out)))
         return out
 
     def bruteforce(self, queries, k):
-        q = np.ascontiguousarray(queries, np.float32)
+        q = np.ascontiguousarray(queries, self.dtype)
         ids = np.empty((q.shape[0], k), np.uint32)
         ds = np.empty((q.shape[0], k), np.float32)
         self._chk(self._L.hnsw_b200_bruteforce(self._h, _p(q), q.shape[0], q.shape[1], k, _p(ids), _p(ds)))

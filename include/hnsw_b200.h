@@ -83,10 +83,76 @@ const Vec_api_Neighbourhood_api* parallel_search_neighbours_f32(const HnswApif32
 /* libext.rs:257-275 (instantiated :771).  Returns 1 on success, -1 on failure. */
 int64_t file_dump_f32(const HnswApif32* hnsw_api, size_t namelen, const uint8_t* filename);
 
+
+/* ---- integer element types (libext.rs:779-1116).  Same pattern as f32; accepted distance names as upstream:
+ * i32: DistL1 DistL2 DistHamming (:779-810) | u32: DistL1 DistL2 DistJaccard DistHamming (:843-881) |
+ * u16: DistL1 DistL2 DistHamming DistJaccard (:914-958; DistLevenshtein is a variable-length edit distance and is not
+ * offered by this engine) | u8: DistL1 DistL2 DistHamming DistJaccard (:1058-1095).
+ * Upstream exports drop_hnsw_f32 and drop_hnsw_u16 only; hnsw_b200_drop() releases a handle of any type. */
+typedef struct HnswApii32 HnswApii32; /* libext.rs:779-835 */
+const HnswApii32* init_hnsw_i32(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname);
+const HnswApii32* init_hnsw_ptrdist_i32(size_t max_nb_conn, size_t ef_const,
+                                        float (*c_func)(const int32_t*, const int32_t*, unsigned long long)); /* always NULL */
+void insert_i32(HnswApii32* hnsw_api, size_t len, const int32_t* data, size_t id);
+void parallel_insert_i32(HnswApii32* hnsw_api, size_t nb_vec, size_t vec_len, const int32_t** datas, const size_t* ids);
+const Neighbourhood_api* search_neighbours_i32(const HnswApii32* hnsw_api, size_t len, const int32_t* data, size_t knbn,
+                                               size_t ef_search);
+const Vec_api_Neighbourhood_api* parallel_search_neighbours_i32(const HnswApii32* hnsw_api, size_t nb_vec,
+                                                                int64_t vec_len, const int32_t** data, size_t knbn,
+                                                                size_t ef_search);
+int64_t file_dump_i32(const HnswApii32* hnsw_api, size_t namelen, const uint8_t* filename);
+typedef struct HnswApiu32 HnswApiu32; /* libext.rs:843-904 */
+const HnswApiu32* init_hnsw_u32(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname);
+const HnswApiu32* init_hnsw_ptrdist_u32(size_t max_nb_conn, size_t ef_const,
+                                        float (*c_func)(const uint32_t*, const uint32_t*, unsigned long long)); /* always NULL */
+void insert_u32(HnswApiu32* hnsw_api, size_t len, const uint32_t* data, size_t id);
+void parallel_insert_u32(HnswApiu32* hnsw_api, size_t nb_vec, size_t vec_len, const uint32_t** datas, const size_t* ids);
+const Neighbourhood_api* search_neighbours_u32(const HnswApiu32* hnsw_api, size_t len, const uint32_t* data, size_t knbn,
+                                               size_t ef_search);
+const Vec_api_Neighbourhood_api* parallel_search_neighbours_u32(const HnswApiu32* hnsw_api, size_t nb_vec,
+                                                                int64_t vec_len, const uint32_t** data, size_t knbn,
+                                                                size_t ef_search);
+int64_t file_dump_u32(const HnswApiu32* hnsw_api, size_t namelen, const uint8_t* filename);
+typedef struct HnswApiu16 HnswApiu16; /* libext.rs:908-1048 */
+const HnswApiu16* init_hnsw_u16(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname);
+const HnswApiu16* init_hnsw_ptrdist_u16(size_t max_nb_conn, size_t ef_const,
+                                        float (*c_func)(const uint16_t*, const uint16_t*, unsigned long long)); /* always NULL */
+void insert_u16(HnswApiu16* hnsw_api, size_t len, const uint16_t* data, size_t id);
+void parallel_insert_u16(HnswApiu16* hnsw_api, size_t nb_vec, size_t vec_len, const uint16_t** datas, const size_t* ids);
+const Neighbourhood_api* search_neighbours_u16(const HnswApiu16* hnsw_api, size_t len, const uint16_t* data, size_t knbn,
+                                               size_t ef_search);
+const Vec_api_Neighbourhood_api* parallel_search_neighbours_u16(const HnswApiu16* hnsw_api, size_t nb_vec,
+                                                                int64_t vec_len, const uint16_t** data, size_t knbn,
+                                                                size_t ef_search);
+int64_t file_dump_u16(const HnswApiu16* hnsw_api, size_t namelen, const uint8_t* filename);
+typedef struct HnswApiu8 HnswApiu8; /* libext.rs:1052-1116 */
+const HnswApiu8* init_hnsw_u8(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname);
+const HnswApiu8* init_hnsw_ptrdist_u8(size_t max_nb_conn, size_t ef_const,
+                                        float (*c_func)(const uint8_t*, const uint8_t*, unsigned long long)); /* always NULL */
+void insert_u8(HnswApiu8* hnsw_api, size_t len, const uint8_t* data, size_t id);
+void parallel_insert_u8(HnswApiu8* hnsw_api, size_t nb_vec, size_t vec_len, const uint8_t** datas, const size_t* ids);
+const Neighbourhood_api* search_neighbours_u8(const HnswApiu8* hnsw_api, size_t len, const uint8_t* data, size_t knbn,
+                                               size_t ef_search);
+const Vec_api_Neighbourhood_api* parallel_search_neighbours_u8(const HnswApiu8* hnsw_api, size_t nb_vec,
+                                                                int64_t vec_len, const uint8_t** data, size_t knbn,
+                                                                size_t ef_search);
+int64_t file_dump_u8(const HnswApiu8* hnsw_api, size_t namelen, const uint8_t* filename);
+const HnswApiu16* new_hnsw_u16(size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname,
+                               size_t max_elements, size_t max_layer); /* libext.rs:964-1028 */
+void drop_hnsw_u16(const HnswApiu16* p);                               /* libext.rs:636-640 */
+
 /* libext.rs:1238-1240.  No-op here (diagnostics go through hnsw_b200_last_error). */
 void init_rust_log(void);
 
-/* ------------------------------------------------------------------ Part 2: extensions */
+/* ------------------------------------------------------------------ Part 2: extensions
+ * `h` is a handle of ANY element type (HnswApif32*, HnswApii32*, HnswApiu32*, HnswApiu16*, HnswApiu8*) passed as
+ * void*; vector / query arguments are arrays of that handle's element type. */
+
+/* dtype: 0 f32, 1 u8, 2 u16, 3 u32, 4 i32.  new_hnsw_<ty> with max_elements / max_layer for every element type. */
+void* hnsw_b200_new(int dtype, size_t max_nb_conn, size_t ef_const, size_t namelen, const uint8_t* cdistname,
+                    size_t max_elements, size_t max_layer);
+void hnsw_b200_drop(const void* h);
+
 
 const char* hnsw_b200_last_error(void);
 int hnsw_b200_device_count(void);
@@ -97,20 +163,20 @@ void hnsw_b200_free_neighbourhood(const Neighbourhood_api* p);
 void hnsw_b200_free_vec_api(const Vec_api_Neighbourhood_api* p);
 
 /* Hnsw setters/getters, /root/reference/src/hnsw.rs:810-905 */
-int hnsw_b200_set_extend_candidates(HnswApif32* h, int flag);  /* hnsw.rs:858 */
-int hnsw_b200_set_keeping_pruned(HnswApif32* h, int flag);     /* hnsw.rs:845 */
-int hnsw_b200_modify_level_scale(HnswApif32* h, double scale); /* hnsw.rs:876-905, scale in [0.2,1] */
-int hnsw_b200_set_searching_mode(HnswApif32* h, int flag);     /* hnsw.rs:834 */
-int hnsw_b200_set_level_seed(HnswApif32* h, uint64_t seed);
-uint64_t hnsw_b200_get_nb_point(const HnswApif32* h);          /* hnsw.rs:810 */
-int hnsw_b200_get_max_level_observed(const HnswApif32* h);     /* hnsw.rs:474 */
-int hnsw_b200_get_dim(const HnswApif32* h);
+int hnsw_b200_set_extend_candidates(void* h, int flag);  /* hnsw.rs:858 */
+int hnsw_b200_set_keeping_pruned(void* h, int flag);     /* hnsw.rs:845 */
+int hnsw_b200_modify_level_scale(void* h, double scale); /* hnsw.rs:876-905, scale in [0.2,1] */
+int hnsw_b200_set_searching_mode(void* h, int flag);     /* hnsw.rs:834 */
+int hnsw_b200_set_level_seed(void* h, uint64_t seed);
+uint64_t hnsw_b200_get_nb_point(const void* h);          /* hnsw.rs:810 */
+int hnsw_b200_get_max_level_observed(const void* h);     /* hnsw.rs:474 */
+int hnsw_b200_get_dim(const void* h);
 /* max in-flight inserts of one GPU batch = clamp(nb_point / ratio, 1, max_batch) (DESIGN.md "batched insert") */
-int hnsw_b200_set_insert_batching(HnswApif32* h, uint32_t ratio, uint32_t max_batch);
+int hnsw_b200_set_insert_batching(void* h, uint32_t ratio, uint32_t max_batch);
 
 /* Flat batched insert: vecs[n][dim] row-major host memory, ids[n] (may be NULL => running index),
  * levels[n] (may be NULL => drawn from the reference's level law, hnsw.rs:363-374). 0 on success. */
-int hnsw_b200_insert_flat(HnswApif32* h, const float* vecs, uint64_t n, uint64_t dim, const uint64_t* ids,
+int hnsw_b200_insert_flat(void* h, const void* vecs, uint64_t n, uint64_t dim, const uint64_t* ids,
                           const int32_t* levels);
 
 /* Flat batched search.  queries[nq][dim] host memory (pinned memory is used directly).
@@ -121,7 +187,7 @@ int hnsw_b200_insert_flat(HnswApif32* h, const float* vecs, uint64_t n, uint64_t
  * list (filter_ids / nfilter), 2 predicate callback evaluated ONCE per stored origin id on the
  * host and materialised to a device bitmap.  0 on success. */
 typedef int (*hnsw_b200_filter_fn)(uint64_t origin_id, void* ctx);
-int hnsw_b200_search_flat(const HnswApif32* h, const float* queries, uint64_t nq, uint64_t dim, uint64_t knbn,
+int hnsw_b200_search_flat(const void* h, const void* queries, uint64_t nq, uint64_t dim, uint64_t knbn,
                           uint64_t ef_search, int filter_mode, const uint64_t* filter_ids, uint64_t nfilter,
                           hnsw_b200_filter_fn fn, void* ctx, uint64_t* out_ids, float* out_dist,
                           uint32_t* out_internal, int32_t* out_pid, int32_t* out_counts);
@@ -131,48 +197,48 @@ int hnsw_b200_search_flat(const HnswApif32* h, const float* queries, uint64_t nq
  * DEVICE pointers owned by the caller; the call enqueues on the index stream and returns without
  * synchronising unless sync != 0.  kernel_ms (may be NULL) receives the CUDA-event duration of the
  * search kernel when sync != 0. */
-int hnsw_b200_search_device(const HnswApif32* h, const float* d_queries, uint64_t nq, uint64_t knbn,
+int hnsw_b200_search_device(const void* h, const void* d_queries, uint64_t nq, uint64_t knbn,
                             uint64_t ef_search, void* d_out, int32_t* d_counts, int sync, float* kernel_ms);
 
 /* Run this handle's kernels and copies on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL
  * restores the handle's own stream), e.g. so that torch.cuda.Event on torch's current stream brackets them. */
-int hnsw_b200_set_stream(HnswApif32* h, void* cuda_stream);
+int hnsw_b200_set_stream(void* h, void* cuda_stream);
 /* After asynchronous hnsw_b200_search_device calls: synchronise and report 1 if a per-warp visited table
  * overflowed (those answers are empty; re-run them with sync != 0, which grows the tables), 0 if not, <0 on error. */
-int hnsw_b200_check_status(HnswApif32* h);
+int hnsw_b200_check_status(void* h);
 
 /* Traversal statistics of all searches since the last reset (device counters):
  * out[0] distance evaluations, out[1] expansions, out[2] adjacency ids read, out[3] queries.
  * Collection is off by default; enable != 0 turns it on. */
-int hnsw_b200_enable_stats(HnswApif32* h, int enable);
-int hnsw_b200_get_stats(const HnswApif32* h, uint64_t* out4, int reset);
+int hnsw_b200_enable_stats(void* h, int enable);
+int hnsw_b200_get_stats(const void* h, uint64_t* out4, int reset);
 
 /* Graph export / import as flat arrays (parity tests, NCCL broadcast, dump writer).
  * Layers are CSR: offsets[nb_point+1], ids[], dists[] (distance to the list owner). */
-int hnsw_b200_export_points(const HnswApif32* h, uint8_t* levels, int32_t* ranks, uint64_t* origin, int64_t* entry);
-int hnsw_b200_export_vectors(const HnswApif32* h, float* out /* [nb_point][dim] */);
-int64_t hnsw_b200_layer_edges(const HnswApif32* h, int layer);
-int hnsw_b200_export_layer(const HnswApif32* h, int layer, uint64_t* offsets, uint32_t* ids, float* dists);
+int hnsw_b200_export_points(const void* h, uint8_t* levels, int32_t* ranks, uint64_t* origin, int64_t* entry);
+int hnsw_b200_export_vectors(const void* h, void* out /* [nb_point][dim] elements */);
+int64_t hnsw_b200_layer_edges(const void* h, int layer);
+int hnsw_b200_export_layer(const void* h, int layer, uint64_t* offsets, uint32_t* ids, float* dists);
 /* import into an EMPTY handle: nlayers CSR layers (layer l at offsets[l], ids[l], dists[l]; dists[l] may be NULL) */
-int hnsw_b200_import_graph(HnswApif32* h, const float* vecs, uint64_t n, uint64_t dim, const uint64_t* origin,
+int hnsw_b200_import_graph(void* h, const void* vecs, uint64_t n, uint64_t dim, const uint64_t* origin,
                            const uint8_t* levels, int64_t entry, int nlayers, const uint64_t* const* offsets,
                            const uint32_t* const* ids, const float* const* dists);
 
 /* Frozen-index blobs in device memory, for replication over NCCL (one rank builds, the others
  * allocate with hnsw_b200_blob_alloc from the broadcast header, then broadcast every blob).
  * header: 16 x uint64 (see DESIGN.md "replication header"). */
-int hnsw_b200_blob_header(const HnswApif32* h, uint64_t* header16);
-int hnsw_b200_blob_alloc(HnswApif32* h, const uint64_t* header16);
-int hnsw_b200_blob_count(const HnswApif32* h);
-int hnsw_b200_blob_info(const HnswApif32* h, int i, void** dev_ptr, uint64_t* nbytes);
-int hnsw_b200_blob_commit(HnswApif32* h); /* after the broadcasts: pull the small host mirrors back */
+int hnsw_b200_blob_header(const void* h, uint64_t* header16);
+int hnsw_b200_blob_alloc(void* h, const uint64_t* header16);
+int hnsw_b200_blob_count(const void* h);
+int hnsw_b200_blob_info(const void* h, int i, void** dev_ptr, uint64_t* nbytes);
+int hnsw_b200_blob_commit(void* h); /* after the broadcasts: pull the small host mirrors back */
 
 /* Stand-alone kernels.  dist_batch: out[nq][m] = dist(queries[i], base[cand[i][j]]) on the index's
  * point store (host pointers).  bruteforce: exact k nearest (ascending) of each query over the
  * index's point store: out_ids are INTERNAL ids. */
-int hnsw_b200_dist_batch(const HnswApif32* h, const float* queries, uint64_t nq, uint64_t dim, const uint32_t* cand,
+int hnsw_b200_dist_batch(const void* h, const void* queries, uint64_t nq, uint64_t dim, const uint32_t* cand,
                          uint64_t m, float* out);
-int hnsw_b200_bruteforce(const HnswApif32* h, const float* queries, uint64_t nq, uint64_t dim, uint64_t k,
+int hnsw_b200_bruteforce(const void* h, const void* queries, uint64_t nq, uint64_t dim, uint64_t k,
                          uint32_t* out_ids, float* out_dist);
 
 #ifdef __cplusplus

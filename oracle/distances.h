@@ -117,12 +117,14 @@ static inline float accumulate_ref(const T* a, const T* b, size_t d) {
 // ORDER_GPU: see header comment.  Mirrors hnswlib-rs_b200/csrc/dist.cuh exactly.
 template <class Acc, class T>
 static inline float accumulate_gpu(const T* a, const T* b, size_t d) {
+  // a 16-byte chunk holds EPC elements (4 x f32/i32/u32, 8 x u16, 16 x u8); lane g owns chunks g, g+8, ...
+  const size_t EPC = 16 / sizeof(T);
   float p[8];
   for (int g = 0; g < 8; ++g) {
     float acc = 0.f;
-    for (size_t c4 = g; 4 * c4 < d; c4 += 8)
-      for (size_t k = 0; k < 4; ++k) {
-        size_t e = 4 * c4 + k;
+    for (size_t c4 = g; EPC * c4 < d; c4 += 8)
+      for (size_t k = 0; k < EPC; ++k) {
+        size_t e = EPC * c4 + k;
         if (e < d) acc = Acc::step(acc, (float)a[e], (float)b[e], true);
       }
     p[g] = acc;

@@ -157,3 +157,69 @@ def test_filtered_search_matches_oracle(pkg, po):
     # through the mirrored single-query API
     res = h.search_filter(Q[0], 10, 64, filter=allow.tolist())
     assert [r.d_id for r in res] == go[0, :gc[0]].tolist()
+
+
+INT_CASES = [
+    # dtype, metric, d, value range
+    (np.uint8, "DistHamming", 48, 4),
+    (np.uint16, "DistHamming", 40, 3),
+    (np.uint32, "DistHamming", 24, 3),
+    (np.int32, "DistHamming", 24, 3),
+    (np.uint8, "DistJaccard", 64, 16),
+    (np.uint16, "DistJaccard", 33, 1000),
+    (np.uint32, "DistJaccard", 20, 100000),
+    (np.uint8, "DistL2", 100, 256),
+    (np.uint16, "DistL1", 30, 5000),
+    (np.int32, "DistL2", 17, 2000),
+]
+
+
+@pytest.mark.parametrize("dtype,metric,d,vrange", INT_CASES)
+def test_integer_types_match_det_oracle(pkg, po, dtype, metric, d, vrange):
+    """integer element types with Hamming / Jaccard / L1 / L2 (libext.rs:779-1116).  Ties are the norm
+    here: the engine orders them by (distance, id) exactly like the oracle's MODE_DET => identical neighbour ids,
+    bit-identical distances; build with one insert in flight => identical graph."""
+    n, M, efc, k, ef = 1500, 8, 48, 10, 32
+    rng = np.random.default_rng(5)
+    lo = -vrange if dtype == np.int32 and metric != "DistHamming" else 0
+    X = rng.integers(lo, vrange, (n, d)).astype(dtype)
+    Q = rng.integers(lo, vrange, (200, d)).astype(dtype)
+    o = po.Oracle(M, n, 16, efc, metric, d, dtype=dtype, mode=po.MODE_DET, order=po.ORDER_GPU)
+    levels = o.draw_levels(n)
+    o.insert_batch(X, levels=levels)
+    h = pkg.Hnsw(M, n, 16, efc, metric, dtype=dtype)
+    h.set_insert_batching(1 << 30, 1)
+    h.insert_flat(X, levels=levels)
+    goff, gids, gds = h.export_layer(0)
+    ooff, oids, ods = o.export_layer(0)
+    assert np.array_equal(goff, ooff) and np.array_equal(gids, oids), "graph differs"
+    assert np.array_equal(gds.view(np.uint32), ods.view(np.uint32))
+    oo, od, oi, opid, oc = o.search_batch(Q, k, ef)
+    go, gd, gi, gpid, gc = h.search_flat(Q, k, ef)
+    assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    # brute force kernel == oracle brute force (ties by id)
+    bi, bd = h.bruteforce(Q[:20], k)
+    ti, td = po.bruteforce(X, Q[:20], k, metric, po.ORDER_GPU)
+    assert np.array_equal(bi, ti) and np.array_equal(bd.view(np.uint32), td.view(np.uint32))
+    # typed reference entry points
+    par = h.parallel_search([q for q in Q[:5]], k, ef)
+    for i in range(5):
+        assert [x.d_id for x in par[i]] == go[i, :gc[i]].tolist()
+
+
+def test_integer_det_vs_std_tie_report(pkg, po):
+    """MODE_STD (Rust-std heap tie behaviour) vs MODE_DET on Hamming data: same distance multiset at the k-th
+    boundary for almost every query; the ids may differ only inside equal-distance groups."""
+    n, d = 2000, 32
+    rng = np.random.default_rng(9)
+    X = rng.integers(0, 3, (n, d)).astype(np.uint8)
+    Q = rng.integers(0, 3, (200, d)).astype(np.uint8)
+    o = po.Oracle(8, n, 16, 64, "DistHamming", d, dtype=np.uint8, mode=po.MODE_DET)
+    o.insert_batch(X)
+    a = o.search_batch(Q, 10, 64)
+    o.set_mode(po.MODE_STD)
+    b = o.search_batch(Q, 10, 64)
+    same_d = np.mean(np.all(a[1] == b[1], axis=1))
+    print("fraction of queries with identical distance lists under std vs det tie rules:", same_d)
+    assert same_d > 0.8

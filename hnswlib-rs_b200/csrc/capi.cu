@@ -36,6 +36,11 @@ static int pass(Index* ix, int r) {
   return r;
 }
 
+#define HB_H(h) \
+  if (!(h)) return set_err("NULL handle"); \
+  Index* ix = ((const AnyApi*)(h))->ix;    \
+  std::lock_guard<std::mutex> g__(ix->mu)
+
 static int metric_from_name(const uint8_t* name, size_t len) {
   std::string s((const char*)name, len);
   if (s == "DistL1") return hb::METRIC_L1;
@@ -224,13 +229,144 @@ void* hnsw_b200_new(int dtype, size_t max_nb_conn, size_t ef_const, size_t namel
 
 }  // extern "C"
 
-static int64_t file_dump_any(const void* hv, size_t, const uint8_t*) {
-  (void)hv;
-  set_err("file_dump: the .hnsw.graph/.hnsw.data writer is SURVEY §8 row f2 (next), not built yet");
-  return -1;
+// generate_file_dump!, libext.rs:257-275: dump into "." with the given basename; 1 on success, -1 on failure
+static int64_t file_dump_any(const void* hv, size_t namelen, const uint8_t* filename) {
+  const AnyApi* h = (const AnyApi*)hv;
+  if (!h || !filename) {
+    set_err("file_dump: NULL argument");
+    return -1;
+  }
+  std::lock_guard<std::mutex> g(h->ix->mu);
+  std::string used;
+  // api.rs:76-78: the reference refuses to overwrite only while a dump is memory-mapped; nothing is mapped here
+  if (pass(h->ix, h->ix->file_dump(".", std::string((const char*)filename, namelen), true, &used))) return -1;
+  return 1;
+}
+
+// HnswIo (hnswio.rs:300-380) reduced to what the C ABI needs: directory + basename
+struct HnswIo {
+  std::string dir, basename;
+};
+
+static void* load_any(HnswIo* io, int dtype, int metric) {
+  if (!io) {
+    set_err("load_hnswdump: NULL HnswIo");
+    return nullptr;
+  }
+  hb::DumpDescription de;
+  std::string e;
+  if (hb::read_description(io->dir + "/" + io->basename + ".hnsw.graph", de, e)) {
+    set_err(e);
+    return nullptr;
+  }
+  const int M = de.max_nb_connection == 0 ? 256 : de.max_nb_connection;
+  Index* ix = new Index(M, (size_t)de.nb_point, 16, (int)de.ef, metric, dtype, g_device);
+  if (!ix->ok() || ix->load_dump(io->dir, io->basename)) {
+    set_err(ix->err());
+    delete ix;
+    return nullptr;  // libext.rs:297-300: failed reload => null
+  }
+  return new AnyApi{ix};
 }
 
 extern "C" {
+
+// get_hnswio, libext.rs:27-33: dump basename, files looked up in the current directory
+HnswIo* get_hnswio(uint64_t flen, const uint8_t* name) {
+  if (!name) return nullptr;
+  return new HnswIo{".", std::string((const char*)name, (size_t)flen)};
+}
+HnswIo* hnsw_b200_get_hnswio(const char* dir, const char* basename) {
+  if (!dir || !basename) return nullptr;
+  return new HnswIo{dir, basename};
+}
+void hnsw_b200_free_hnswio(HnswIo* io) { delete io; }
+
+// generate_loadhnsw!, libext.rs:280-451: one loader per (element type, distance) pair upstream instantiates
+#define HB_LOADER(SUF, DIST, DT, METRIC)                                             \
+  const HnswApi##SUF* load_hnswdump_##SUF##_##DIST(HnswIo* io) {                     \
+    return (const HnswApi##SUF*)load_any(io, DT, METRIC);                            \
+  }
+HB_LOADER(f32, DistL1, hb::DT_F32, hb::METRIC_L1)
+HB_LOADER(f32, DistL2, hb::DT_F32, hb::METRIC_L2)
+HB_LOADER(f32, DistCosine, hb::DT_F32, hb::METRIC_COSINE)
+HB_LOADER(f32, DistDot, hb::DT_F32, hb::METRIC_DOT)
+HB_LOADER(f32, DistJensenShannon, hb::DT_F32, hb::METRIC_JENSENSHANNON)
+HB_LOADER(f32, DistJeffreys, hb::DT_F32, hb::METRIC_JEFFREYS)
+HB_LOADER(i32, DistL1, hb::DT_I32, hb::METRIC_L1)
+HB_LOADER(i32, DistL2, hb::DT_I32, hb::METRIC_L2)
+HB_LOADER(i32, DistHamming, hb::DT_I32, hb::METRIC_HAMMING)
+HB_LOADER(u32, DistL1, hb::DT_U32, hb::METRIC_L1)
+HB_LOADER(u32, DistL2, hb::DT_U32, hb::METRIC_L2)
+HB_LOADER(u32, DistHamming, hb::DT_U32, hb::METRIC_HAMMING)
+HB_LOADER(u32, DistJaccard, hb::DT_U32, hb::METRIC_JACCARD)
+HB_LOADER(u16, DistL1, hb::DT_U16, hb::METRIC_L1)
+HB_LOADER(u16, DistL2, hb::DT_U16, hb::METRIC_L2)
+HB_LOADER(u16, DistHamming, hb::DT_U16, hb::METRIC_HAMMING)
+HB_LOADER(u8, DistL1, hb::DT_U8, hb::METRIC_L1)
+HB_LOADER(u8, DistL2, hb::DT_U8, hb::METRIC_L2)
+HB_LOADER(u8, DistHamming, hb::DT_U8, hb::METRIC_HAMMING)
+HB_LOADER(u8, DistJaccard, hb::DT_U8, hb::METRIC_JACCARD)
+#undef HB_LOADER
+
+// load any (element type, distance) by name: dtype 0 f32, 1 u8, 2 u16, 3 u32, 4 i32
+void* hnsw_b200_load_dump(HnswIo* io, int dtype, size_t namelen, const uint8_t* cdistname) {
+  if (!cdistname) return nullptr;
+  const int metric = metric_from_name(cdistname, namelen);
+  if (metric < 0 || !hb::metric_supported(metric, dtype)) {
+    set_err("unknown / unsupported distance name for this element type");
+    return nullptr;
+  }
+  return load_any(io, dtype, metric);
+}
+
+int hnsw_b200_file_dump(const void* h, const char* dir, const char* basename, int overwrite, char* used_basename,
+                        size_t used_cap) {
+  HB_H(h);
+  if (!dir || !basename) return set_err("NULL path");
+  std::string used;
+  int r = pass(ix, ix->file_dump(dir, basename, overwrite != 0, &used));
+  if (r) return r;
+  if (used_basename && used_cap) {
+    strncpy(used_basename, used.c_str(), used_cap - 1);
+    used_basename[used_cap - 1] = 0;
+  }
+  return 0;
+}
+
+// load_hnsw_description, libext.rs:1170-1232.  `name` = path of the .hnsw.graph file.  Release with
+// hnsw_b200_free_description (upstream leaks it).
+const DescriptionFFI* load_hnsw_description(size_t flen, const uint8_t* name) {
+  if (!name) return nullptr;
+  hb::DumpDescription de;
+  std::string e;
+  if (hb::read_description(std::string((const char*)name, flen), de, e)) {
+    set_err(e);
+    return nullptr;
+  }
+  DescriptionFFI* d = (DescriptionFFI*)calloc(1, sizeof(DescriptionFFI));
+  d->dumpmode = 1;  // upstream hard-codes 1 here ("CAVEAT", libext.rs:1196)
+  d->max_nb_connection = de.max_nb_connection;
+  d->nb_layer = de.nb_layer;
+  d->ef = (size_t)de.ef;
+  d->nb_point = (size_t)de.nb_point;  // upstream leaves this field at 0; filled here
+  d->data_dimension = (size_t)de.dimension;
+  char* dn = (char*)malloc(de.distname.size() + 1);
+  memcpy(dn, de.distname.c_str(), de.distname.size() + 1);
+  char* tn = (char*)malloc(de.t_name.size() + 1);
+  memcpy(tn, de.t_name.c_str(), de.t_name.size() + 1);
+  d->distname_len = de.distname.size();
+  d->distname = (const uint8_t*)dn;
+  d->t_name_len = de.t_name.size();
+  d->t_name = (const uint8_t*)tn;
+  return d;
+}
+void hnsw_b200_free_description(const DescriptionFFI* d) {
+  if (!d) return;
+  free((void*)d->distname);
+  free((void*)d->t_name);
+  free((void*)d);
+}
 
 void init_rust_log(void) {}
 
@@ -264,10 +400,6 @@ void hnsw_b200_free_vec_api(const Vec_api_Neighbourhood_api* p) {
   free(box);
 }
 
-#define HB_H(h) \
-  if (!(h)) return set_err("NULL handle"); \
-  Index* ix = ((const AnyApi*)(h))->ix;    \
-  std::lock_guard<std::mutex> g__(ix->mu)
 
 int hnsw_b200_set_extend_candidates(void* h, int flag) {
   HB_H(h);

@@ -32,6 +32,18 @@ struct DevArray {  // growable device array, contents preserved on growth
   size_t cap = 0;
 };
 
+struct DumpDescription {  // Description, /root/reference/src/hnswio.rs:846-870
+  int format_version = 0;
+  uint8_t dumpmode = 0, max_nb_connection = 0, nb_layer = 0;
+  double level_scale = 1.0;
+  uint64_t ef = 0, nb_point = 0, dimension = 0;
+  std::string distname, t_name;
+  long header_bytes = 0;
+};
+int read_description(const std::string& graph_path, DumpDescription& out, std::string& err);
+int metric_from_type_name(const std::string& full);
+int dtype_from_type_name(const std::string& s);
+
 class Index {
  public:
   Index(int M, size_t max_elements, int max_layer, int ef_c, int metric, int dtype, int device);
@@ -77,6 +89,9 @@ class Index {
 
   int export_layer(int layer, uint64_t* offsets, uint32_t* ids, float* dists, int64_t* total) const;
   int export_vectors(void* out) const;
+  // dump / reload in the reference's two-file format (hnswio.cu)
+  int file_dump(const std::string& dir, const std::string& basename, bool overwrite, std::string* used_basename);
+  int load_dump(const std::string& dir, const std::string& basename);
   int enable_stats(bool on);
   int get_stats(uint64_t* out4, bool reset);
 

@@ -54,6 +54,17 @@ def load_library():
     for suf in ("f32", "u16"):
         f = getattr(L, "new_hnsw_" + suf); f.restype = vp; f.argtypes = [sz, sz, sz, C.c_char_p, sz, sz]
         getattr(L, "drop_hnsw_" + suf).argtypes = [vp]
+    L.get_hnswio.restype = vp
+    L.get_hnswio.argtypes = [u64, C.c_char_p]
+    L.hnsw_b200_get_hnswio.restype = vp
+    L.hnsw_b200_get_hnswio.argtypes = [C.c_char_p, C.c_char_p]
+    L.hnsw_b200_free_hnswio.argtypes = [vp]
+    L.hnsw_b200_file_dump.argtypes = [vp, C.c_char_p, C.c_char_p, i32, C.c_char_p, sz]
+    L.hnsw_b200_load_dump.restype = vp
+    L.hnsw_b200_load_dump.argtypes = [vp, i32, sz, C.c_char_p]
+    L.load_hnsw_description.restype = vp
+    L.load_hnsw_description.argtypes = [sz, C.c_char_p]
+    L.hnsw_b200_free_description.argtypes = [vp]
     L.hnsw_b200_new.restype = vp
     L.hnsw_b200_new.argtypes = [i32, sz, sz, sz, C.c_char_p, sz, sz]
     L.hnsw_b200_drop.argtypes = [vp]
@@ -303,12 +314,36 @@ class Hnsw:
                                                 _p(o), _p(ds), _p(it), _p(pid), _p(cnt)))
         return o, ds, it, pid, cnt
 
-    def file_dump(self, path, basename):
+    def file_dump(self, path, basename, overwrite=True):
+        """AnnT::file_dump (api.rs:70-93): writes <basename>.hnsw.graph / .hnsw.data under `path`, returns the basename
+        actually used (a unique one when overwrite is False and the data file exists)."""
+        used = C.create_string_buffer(4096)
+        self._chk(self._L.hnsw_b200_file_dump(self._h, str(path).encode(), basename.encode(), int(bool(overwrite)), used, 4096))
+        return used.value.decode()
+
+    def file_dump_cwd(self, basename):
+        """the reference C entry point file_dump_<ty>: dumps into the current directory, returns 1 / -1"""
         name = basename.encode()
-        r = getattr(self._L, "file_dump_" + self._suf)(self._h, len(name), name)
-        if r != 1:
-            raise HnswError("file_dump_f32 failed: " + last_error())
-        return basename
+        return int(getattr(self._L, "file_dump_" + self._suf)(self._h, len(name), name))
+
+    @classmethod
+    def load(cls, path, basename, dist_name, dtype=np.float32, device=None):
+        """HnswIo::load_hnsw::<T, D> (hnswio.rs:431-524) through hnsw_b200_get_hnswio + hnsw_b200_load_dump."""
+        L = load_library()
+        if device is not None and L.hnsw_b200_set_device(int(device)) != 0:
+            raise HnswError(last_error())
+        io = L.hnsw_b200_get_hnswio(str(path).encode(), basename.encode())
+        name = dist_name.encode()
+        h = L.hnsw_b200_load_dump(io, _DT[np.dtype(dtype)][0], len(name), name)
+        L.hnsw_b200_free_hnswio(io)
+        if not h:
+            raise HnswError("load failed: " + last_error())
+        self = cls.__new__(cls)
+        self._L, self._h, self.dtype, self.dist_name = L, h, np.dtype(dtype), dist_name
+        self._suf = _DT[self.dtype][1]
+        self.max_nb_connection = None
+        self.ef_construction = None
+        return self
 
     # ---- statistics / graph transfer (extensions)
     def enable_stats(self, on=True):

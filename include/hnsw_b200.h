@@ -141,6 +141,47 @@ const HnswApiu16* new_hnsw_u16(size_t max_nb_conn, size_t ef_const, size_t namel
                                size_t max_elements, size_t max_layer); /* libext.rs:964-1028 */
 void drop_hnsw_u16(const HnswApiu16* p);                               /* libext.rs:636-640 */
 
+/* ---- dump reload (libext.rs:27-33, 280-451, 1121-1232).  Files: <basename>.hnsw.graph + <basename>.hnsw.data in the
+ * reference's native format (hnswio.rs), so dumps written by hnsw_rs load here and the other way round. */
+typedef struct HnswIo HnswIo;
+HnswIo* get_hnswio(uint64_t flen, const uint8_t* name); /* libext.rs:27-33: basename, looked up in "." */
+const HnswApif32* load_hnswdump_f32_DistL1(HnswIo* io); /* libext.rs:310-345 */
+const HnswApif32* load_hnswdump_f32_DistL2(HnswIo* io);
+const HnswApif32* load_hnswdump_f32_DistCosine(HnswIo* io);
+const HnswApif32* load_hnswdump_f32_DistDot(HnswIo* io);
+const HnswApif32* load_hnswdump_f32_DistJensenShannon(HnswIo* io);
+const HnswApif32* load_hnswdump_f32_DistJeffreys(HnswIo* io);
+const HnswApii32* load_hnswdump_i32_DistL1(HnswIo* io); /* libext.rs:348-365 */
+const HnswApii32* load_hnswdump_i32_DistL2(HnswIo* io);
+const HnswApii32* load_hnswdump_i32_DistHamming(HnswIo* io);
+const HnswApiu32* load_hnswdump_u32_DistL1(HnswIo* io); /* libext.rs:368-391 */
+const HnswApiu32* load_hnswdump_u32_DistL2(HnswIo* io);
+const HnswApiu32* load_hnswdump_u32_DistHamming(HnswIo* io);
+const HnswApiu32* load_hnswdump_u32_DistJaccard(HnswIo* io);
+const HnswApiu16* load_hnswdump_u16_DistL1(HnswIo* io); /* libext.rs:394-417 (DistLevenshtein: not offered) */
+const HnswApiu16* load_hnswdump_u16_DistL2(HnswIo* io);
+const HnswApiu16* load_hnswdump_u16_DistHamming(HnswIo* io);
+const HnswApiu8* load_hnswdump_u8_DistL1(HnswIo* io); /* libext.rs:420-443 */
+const HnswApiu8* load_hnswdump_u8_DistL2(HnswIo* io);
+const HnswApiu8* load_hnswdump_u8_DistHamming(HnswIo* io);
+const HnswApiu8* load_hnswdump_u8_DistJaccard(HnswIo* io);
+
+/* libext.rs:1121-1141   #[repr(C)] pub struct DescriptionFFI (64 bytes) */
+typedef struct DescriptionFFI {
+  uint8_t dumpmode;
+  uint8_t max_nb_connection;
+  uint8_t nb_layer;
+  size_t ef;
+  size_t nb_point;
+  size_t data_dimension;
+  size_t distname_len;
+  const uint8_t* distname;
+  size_t t_name_len;
+  const uint8_t* t_name;
+} DescriptionFFI;
+/* libext.rs:1170-1232; `name` is the path of the .hnsw.graph file */
+const DescriptionFFI* load_hnsw_description(size_t flen, const uint8_t* name);
+
 /* libext.rs:1238-1240.  No-op here (diagnostics go through hnsw_b200_last_error). */
 void init_rust_log(void);
 
@@ -206,6 +247,15 @@ int hnsw_b200_set_stream(void* h, void* cuda_stream);
 /* After asynchronous hnsw_b200_search_device calls: synchronise and report 1 if a per-warp visited table
  * overflowed (those answers are empty; re-run them with sync != 0, which grows the tables), 0 if not, <0 on error. */
 int hnsw_b200_check_status(void* h);
+
+/* Dump helpers: explicit directory, overwrite flag (DumpInit, hnswio.rs:150-236: with overwrite = 0 an existing
+ * <basename>.hnsw.data is kept and a unique "<basename>-<n>" is used; it is returned in used_basename), loaders by name. */
+HnswIo* hnsw_b200_get_hnswio(const char* dir, const char* basename);
+void hnsw_b200_free_hnswio(HnswIo* io);
+int hnsw_b200_file_dump(const void* h, const char* dir, const char* basename, int overwrite, char* used_basename,
+                        size_t used_cap);
+void* hnsw_b200_load_dump(HnswIo* io, int dtype, size_t namelen, const uint8_t* cdistname);
+void hnsw_b200_free_description(const DescriptionFFI* d);
 
 /* Traversal statistics of all searches since the last reset (device counters):
  * out[0] distance evaluations, out[1] expansions, out[2] adjacency ids read, out[3] queries.

@@ -14,7 +14,7 @@ def declared_symbols():
     src = open(os.path.join(ROOT, "include", "hnsw_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = re.findall(r"\b([a-zA-Z_][a-zA-Z0-9_]*)\s*\(", src)
-    pat = re.compile(r"^(init_|new_hnsw|drop_hnsw|insert_|parallel_|search_neighbours|file_dump|hnsw_b200_)")
+    pat = re.compile(r"^(init_|new_hnsw|drop_hnsw|insert_|parallel_|search_neighbours|file_dump|load_hnsw|get_hnswio|hnsw_b200_)")
     out = []
     for n in names:
         if not pat.match(n) or n.startswith("hnsw_b200_filter_fn"):
@@ -27,7 +27,7 @@ def declared_symbols():
 def test_library_exports_every_declared_symbol(pkg):
     L = pkg.load_library()
     syms = declared_symbols()
-    assert "parallel_search_neighbours_f32" in syms and "parallel_insert_f32" in syms and len(syms) > 35
+    assert "parallel_search_neighbours_f32" in syms and "parallel_insert_f32" in syms and len(syms) > 90
     for s in syms:
         assert hasattr(L, s), f"libhnsw_b200.so does not export {s}"
 

@@ -362,7 +362,8 @@ cudaError_t launch_insert_search(const InsertParams& p, int metric, int dtype, i
   return dispatch_op(metric, dtype, [&](auto tag) -> cudaError_t {
     using Op = typename decltype(tag)::type;
     if constexpr (Specialise<Op>::value) {
-      if (p.q_smem == 0) return launch_insert_for_op<Op, 8>(p, grid, smem, st, query_only, blocks_per_sm);
+      if (p.q_kind == 108) return launch_insert_for_op<Op, 108>(p, grid, smem, st, query_only, blocks_per_sm);
+      if (p.q_kind == 104) return launch_insert_for_op<Op, 104>(p, grid, smem, st, query_only, blocks_per_sm);
     }
     return launch_insert_for_op<Op, 0>(p, grid, smem, st, query_only, blocks_per_sm);
   });

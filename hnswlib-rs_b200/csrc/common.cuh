@@ -650,6 +650,73 @@ struct SortedQueue {
   }
 };
 
+// SortedQueue with a compile-time number of 32-entry chunks (capacity 32*NCH >= ef): no loops, no bounds tests
+// (unused slots hold ~0, which compares above every key and reads as "expanded"), one __syncwarp per update.
+template <int NCH>
+struct SmemQueueN {
+  uint64_t* w;
+  int n;
+  int cap;
+
+  __device__ __forceinline__ void reset(uint64_t* buf, int ef) {
+    w = buf;
+    n = 0;
+    cap = ef;
+    const int lane = lane_id();
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) w[32 * c + lane] = ~0ull;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void clear() { reset(w, cap); }
+  __device__ __forceinline__ uint64_t get(int i) const { return w[i]; }
+  __device__ __forceinline__ uint64_t local(int i) const { return w[i]; }
+  __device__ __forceinline__ void mark_expanded(int i) {
+    if (lane_id() == 0) w[i] |= 1ull;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void push_first(uint64_t key) {
+    if (lane_id() == 0) w[0] = key;
+    n = 1;
+    __syncwarp();
+  }
+  __device__ __forceinline__ int first_unexpanded() const { return next_unexpanded(0); }
+  __device__ __forceinline__ int next_unexpanded(int from) const {
+    const int lane = lane_id();
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int i = 32 * c + lane;
+      const unsigned m = __ballot_sync(FULL, ((w[i] & 1ull) == 0ull) && i >= from);
+      if (m) return 32 * c + __ffs(m) - 1;
+    }
+    return -1;
+  }
+  // when the queue is not full its last slot holds ~0, so one comparison covers both cases
+  __device__ __forceinline__ bool accepts(uint64_t key) const { return key < (w[cap - 1] & ~1ull); }
+  __device__ __forceinline__ void insert(uint64_t key) {
+    const int lane = lane_id();
+    uint64_t cur[NCH], prev[NCH];
+    int pos = 0;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int i = 32 * c + lane;
+      cur[c] = w[i];
+      prev[c] = i > 0 ? w[i - 1] : 0ull;
+      pos += __popc(__ballot_sync(FULL, cur[c] < key));
+    }
+    __syncwarp();  // every lane has read its sources
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int i = 32 * c + lane;
+      uint64_t nv = i > pos ? prev[c] : key;
+      if (i >= cap) nv = ~0ull;
+      if (i >= pos) w[i] = nv;
+    }
+    __syncwarp();
+    n = n < cap ? n + 1 : cap;
+  }
+};
+
 // Same queue held in registers: entry i lives in lane (i & 31), stripe (i >> 5); unused slots hold ~0 (whose
 // low bit reads as "expanded", so scans skip them).  Sorted insert = ballot rank + one shuffle-up per stripe.
 // No shared-memory traffic and no __syncwarp on the hot path.  Capacity 32*NS >= ef.
@@ -726,13 +793,15 @@ struct RegQueue {
   }
 };
 
-template <int NS>
+// queue kinds: 0 = generic SortedQueue (any ef), 100 + NCH = SmemQueueN<NCH> (ef <= 32*NCH), other = RegQueue<NS>
+template <int KIND>
 struct QueueSel {
-  typedef RegQueue<NS> type;
+  typedef RegQueue<KIND> type;
 };
-template <>
-struct QueueSel<0> {
-  typedef SortedQueue type;
-};
+template <> struct QueueSel<0> { typedef SortedQueue type; };
+template <> struct QueueSel<101> { typedef SmemQueueN<1> type; };
+template <> struct QueueSel<102> { typedef SmemQueueN<2> type; };
+template <> struct QueueSel<104> { typedef SmemQueueN<4> type; };
+template <> struct QueueSel<108> { typedef SmemQueueN<8> type; };
 
 }  // namespace hb

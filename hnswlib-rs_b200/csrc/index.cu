@@ -254,8 +254,9 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
   p.locks = d_locks_.p;
   p.stats = nullptr;
   p.status = d_status_;
-  // the insert kernel keeps its queue in registers (8 stripes) when ef_construction <= 256
-  p.q_smem = (queue_stripes(ef_c, metric) != 0 && ef_c <= 256) ? 0 : ef_c;
+  p.q_kind = queue_kind(ef_c, metric, dtype);
+  if (p.q_kind != 0 && p.q_kind < 104) p.q_kind = 104;  // the insert kernel is built for 128 / 256-slot queues only
+  p.q_smem = queue_slots(p.q_kind, ef_c);
   const size_t spw = insert_smem_per_warp(p.g.d4, ef_c, p.g.deg0, p.q_smem);
   p.smem_per_warp = (int)spw;
   const size_t smem = spw * (BUILD_THREADS / 32);
@@ -523,7 +524,8 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
   p.stats = stats_on_ ? d_stats_ : nullptr;
   p.status = d_status_;
   const bool filtered = d_filter_bits != nullptr;
-  p.q_smem = (!filtered && queue_stripes(p.ef, metric) != 0) ? 0 : p.ef;
+  p.q_kind = filtered ? 0 : queue_kind(p.ef, metric, dtype);
+  p.q_smem = queue_slots(p.q_kind, p.ef);
   size_t spw = search_smem_per_warp(p.g.d4, p.q_smem);
   p.smem_per_warp = (int)spw;
   const int wpb = SEARCH_THREADS / 32;

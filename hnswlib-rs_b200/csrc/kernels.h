@@ -39,7 +39,8 @@ struct SearchParams {
   unsigned long long* stats;    // nullptr or [3]: evals, expansions, adjacency ids read
   int* status;                  // set to 1 on visited-table overflow
   int smem_per_warp;
-  int q_smem;  // queue slots kept in shared memory (0 when the queue lives in registers)
+  int q_smem;  // queue slots in shared memory
+  int q_kind;  // QueueSel kind
   uint64_t* cbuf;  // filtered search only: candidate queue C, [slots][ccap] keys
   uint32_t ccap;
 };
@@ -47,17 +48,18 @@ struct SearchParams {
 // rows of up to 512 bytes are (partly) staged by TMA: STAGE_ROWS rows + an mbarrier per warp
 __host__ __device__ inline size_t stage_bytes(int d4) { return d4 <= 32 ? (size_t)STAGE_ROWS * d4 * 16 : 0; }
 // register-queue stripes for a given ef (0 = queue in shared memory)
-// Measured on B200 (profiles/README.md): at 64 registers/thread the register queue spills and is ~5 % slower than
-// the shared-memory queue, so it is opt-in (HNSW_B200_REGQUEUE=1) until the kernel's register budget changes.
-inline int queue_stripes(int ef, int metric) {
-  static const bool enabled = [] { const char* e = getenv("HNSW_B200_REGQUEUE"); return e && e[0] == '1'; }();
-  if (!enabled) return 0;
-  const bool common = metric == METRIC_L1 || metric == METRIC_L2 || metric == METRIC_DOT || metric == METRIC_COSINE;
-  if (!common) return 0;
-  if (ef <= 64) return 2;
-  if (ef <= 256) return 8;
-  return 0;
+// Queue kind for a given ef (see QueueSel): compile-time chunked shared-memory queue up to ef = 256, generic beyond.
+// (A register-resident variant, RegQueue, exists in common.cuh; measured ~5 % slower at 64 registers/thread because
+// it spills, so it is not instantiated.)
+inline int queue_kind(int ef, int metric, int dtype) {
+  const bool common = dtype == DT_F32 && (metric == METRIC_L1 || metric == METRIC_L2 || metric == METRIC_DOT || metric == METRIC_COSINE);
+  if (!common || ef > 256) return 0;
+  if (ef <= 32) return 101;
+  if (ef <= 64) return 102;
+  if (ef <= 128) return 104;
+  return 108;
 }
+inline int queue_slots(int kind, int ef) { return kind >= 100 ? 32 * (kind - 100) : ef; }
 inline size_t search_smem_per_warp(int d4, int q_smem) {
   size_t b = stage_bytes(d4) + (size_t)d4 * 16 + (size_t)q_smem * 8 + 32 * 8 + 16;
   return (b + 127) & ~(size_t)127;
@@ -78,6 +80,7 @@ struct InsertParams {
   int* status;
   int smem_per_warp;
   int q_smem;
+  int q_kind;
 };
 
 inline size_t insert_smem_per_warp(int d4, int ef_c, int deg0, int q_smem) {

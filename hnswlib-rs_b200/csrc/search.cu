@@ -150,9 +150,10 @@ cudaError_t launch_search(const SearchParams& p, int metric, int dtype, int grid
   return dispatch_op(metric, dtype, [&](auto tag) -> cudaError_t {
     using Op = typename decltype(tag)::type;
     if constexpr (Specialise<Op>::value) {
-      const int ns = p.q_smem ? 0 : queue_stripes(p.ef, METRIC_L2);
-      if (ns == 2) return launch_for_op<Op, 2>(p, grid, smem, st, query_only, blocks_per_sm);
-      if (ns == 8) return launch_for_op<Op, 8>(p, grid, smem, st, query_only, blocks_per_sm);
+      if (p.q_kind == 101) return launch_for_op<Op, 101>(p, grid, smem, st, query_only, blocks_per_sm);
+      if (p.q_kind == 102) return launch_for_op<Op, 102>(p, grid, smem, st, query_only, blocks_per_sm);
+      if (p.q_kind == 104) return launch_for_op<Op, 104>(p, grid, smem, st, query_only, blocks_per_sm);
+      if (p.q_kind == 108) return launch_for_op<Op, 108>(p, grid, smem, st, query_only, blocks_per_sm);
     }
     return launch_for_op<Op, 0>(p, grid, smem, st, query_only, blocks_per_sm);
   });

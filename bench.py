@@ -139,6 +139,10 @@ def recall_stats(ids, dists, counts, t_ids, t_d):
     return rid / t_ids.shape[0], rball / t_ids.shape[0]
 
 
+def default_workload(a):
+    return (a.n, a.d, a.nq, a.M, a.efc, a.k, a.ef, a.metric, a.data) == (1000000, 128, 10000, 16, 200, 10, 64, "DistL2", "clustered")
+
+
 def workload_name(a):
     return (f"SIFT1M-shape synthetic ({a.data}): {a.n} x d={a.d} f32 {a.metric}, M={a.M} ef_c={a.efc}, "
             f"{a.nq} queries/step/GPU k={a.k} ef={a.ef}")
@@ -172,7 +176,8 @@ def run_reference(a, rank, world):
     qps = a.steps * a.nq / dt
     nt = min(1000, a.nq)
     ti, td = po.bruteforce(X, Q[:nt], a.k, a.metric)
-    rid, rball = recall_stats(res[2][:nt], res[1][:nt], res[4][:nt], ti, td)
+    # origin ids == row numbers of X; internal ids are NOT (a racy parallel insert numbers points in arrival order)
+    rid, rball = recall_stats(res[0][:nt], res[1][:nt], res[4][:nt], ti, td)
     line = {
         "impl": "reference", "metric": "queries/sec @ recall@10", "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
@@ -327,7 +332,7 @@ def run_ours(a, rank, world, local_rank):
                 "d2h_bytes_per_step": a.nq * a.k * 16 + a.nq * 4},
         "gpu_launches": a.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src, "kernel": "search_kernel",
+                     "traffic": TRAFFIC_BYTES_PER_LAUNCH if default_workload(a) else None, "peak_source": peak_src, "kernel": "search_kernel",
                      "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per_query * a.nq},
     }
     if world == 1 and not a.no_cpu_baseline:
@@ -336,9 +341,9 @@ def run_ours(a, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one search_kernel launch on the default workload, from the
-# ncu --set full capture summarised in profiles/ (null until a capture of the current kernel exists)
-TRAFFIC_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum of one search_kernel launch on the DEFAULT workload, from the
+# ncu --set full capture summarised in profiles/ (reported only when the run uses the default workload)
+TRAFFIC_BYTES_PER_LAUNCH = 6.476e9   # profiles/r1_final_search_kernel_ncu_full_selected.csv: 6.127 GB read + 0.349 GB written
 
 
 def cpu_baseline(a, h, Q):

@@ -45,9 +45,9 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
   s.wbuf = reinterpret_cast<uint64_t*>(base + off);
   off += (size_t)p.q_smem * 8;
   s.cand_id = reinterpret_cast<uint32_t*>(base + off);
-  off += 128;
+  off += 256;
   s.cand_d = reinterpret_cast<float*>(base + off);
-  off += 128;
+  off += 256;
   stg.bar = reinterpret_cast<uint64_t*>(base + off);
   off += 16;
   stg.phase = 0;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
     // ---- layers level..0: ef_construction search + selection (hnsw.rs:1158-1205)
     for (int l = lv; l >= 0 && !overflow; --l) {
       if (!((mask >> l) & 1u)) continue;
-      search_layer<Op, CH, U, Queue>(g, s, stg, vis, Q, cur, p.ef_c, l, st, overflow);
+      search_layer<Op, CH, U, Queue>(g, s, stg, vis, Q, cur, p.ef_c, l, st, overflow, p.count - wi <= p.spec_tail);
       if (overflow) break;
       const int n = Q.n;
       const int nb = (l == 0) ? g.deg0 : g.M;  // 1177-1183

@@ -559,6 +559,26 @@ struct Visited {
     used += __popc(__ballot_sync(FULL, fresh));  // warp-uniform count
     return fresh;
   }
+  // Warp-collective read-only membership test (exact): true in the lanes whose id is in the set.
+  __device__ __forceinline__ bool contains(uint32_t id, bool valid) const {
+    const uint32_t want = tag | id;
+    uint32_t h = (id * 2654435761u) >> shift;
+    bool pending = valid, found = false;
+    while (__any_sync(FULL, pending)) {
+      if (pending) {
+        const uint32_t cur = __ldcg(tab + h);
+        if (cur == want) {
+          found = true;
+          pending = false;
+        } else if ((cur >> id_bits) != epoch) {
+          pending = false;  // free slot ends the probe chain: not present
+        } else {
+          h = (h + 1) & mask;
+        }
+      }
+    }
+    return found;
+  }
   __device__ __forceinline__ bool overflowing() const { return used >= limit; }
 };
 

@@ -16,6 +16,14 @@ namespace hb {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
+// Last-wave speculation threshold = slots * pct / 100.  Measured on B200 (profiles/README.md): speculation is exact
+// but never faster (2.04 ms -> 2.15-2.20 ms per 10k queries for pct = 50..150), so it is OFF unless
+// HNSW_B200_SPEC_TAIL=<pct> asks for it.
+static uint32_t spec_tail_items(size_t slots) {
+  static const int pct = [] { const char* e = getenv("HNSW_B200_SPEC_TAIL"); return e ? atoi(e) : 0; }();
+  return (uint32_t)(slots * (size_t)pct / 100);
+}
+
 static size_t next_pow2(size_t x) {
   size_t p = 1;
   while (p < x) p <<= 1;
@@ -271,6 +279,7 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
     int r;
     if ((r = ensure_visited((size_t)grid * wpb, vcap))) return r;
     if ((r = fill_visited_cfg(p.vis))) return r;
+    p.spec_tail = spec_tail_items((size_t)grid * wpb);
     HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
     HB_CUDA(launch_insert_search(p, metric, dtype, grid, smem, stream_, false, nullptr));
     int status = 0;
@@ -537,6 +546,7 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
   if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, 0, smem, stream_, true, &bps));
   else HB_CUDA(launch_search(p, metric, dtype, 0, smem, stream_, true, &bps));
   if (bps < 1) return fail("search kernel does not fit on an SM");
+  if (const char* e = getenv("HNSW_B200_SEARCH_CTAS")) bps = std::max(1, std::min(bps, atoi(e)));  // tuning knob
   int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (nq + wpb - 1) / wpb);
   const int deg = layer0 == 0 ? 2 * M : M;
   size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)2 * (p.ef + 16) * deg));
@@ -556,6 +566,7 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
       p.cbuf = (uint64_t*)d_cbuf_;
       p.ccap = (uint32_t)vis_cap_;
     }
+    p.spec_tail = spec_tail_items((size_t)grid * wpb);
     HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
     HB_CUDA(cudaEventRecord(ev0_, stream_));
     if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, grid, smem, stream_, false, nullptr));

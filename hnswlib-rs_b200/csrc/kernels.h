@@ -41,6 +41,7 @@ struct SearchParams {
   int smem_per_warp;
   int q_smem;  // queue slots in shared memory
   int q_kind;  // QueueSel kind
+  uint32_t spec_tail;  // work items with fewer than this many items left after them speculate (last wave)
   uint64_t* cbuf;  // filtered search only: candidate queue C, [slots][ccap] keys
   uint32_t ccap;
 };
@@ -61,7 +62,7 @@ inline int queue_kind(int ef, int metric, int dtype) {
 }
 inline int queue_slots(int kind, int ef) { return kind >= 100 ? 32 * (kind - 100) : ef; }
 inline size_t search_smem_per_warp(int d4, int q_smem) {
-  size_t b = stage_bytes(d4) + (size_t)d4 * 16 + (size_t)q_smem * 8 + 32 * 8 + 16;
+  size_t b = stage_bytes(d4) + (size_t)d4 * 16 + (size_t)q_smem * 8 + 64 * 8 + 16;
   return (b + 127) & ~(size_t)127;
 }
 
@@ -81,10 +82,11 @@ struct InsertParams {
   int smem_per_warp;
   int q_smem;
   int q_kind;
+  uint32_t spec_tail;
 };
 
 inline size_t insert_smem_per_warp(int d4, int ef_c, int deg0, int q_smem) {
-  size_t b = stage_bytes(d4) + (size_t)d4 * 32 + (size_t)q_smem * 8 + 256 + 16 + (size_t)deg0 * 12 + (size_t)ef_c * 2;
+  size_t b = stage_bytes(d4) + (size_t)d4 * 32 + (size_t)q_smem * 8 + 512 + 16 + (size_t)deg0 * 12 + (size_t)ef_c * 2;
   return (b + 127) & ~(size_t)127;
 }
 

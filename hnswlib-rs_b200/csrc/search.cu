@@ -20,10 +20,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
   s.q4 = reinterpret_cast<uint4*>(base + stb);
   s.wbuf = reinterpret_cast<uint64_t*>(base + stb + (size_t)g.d4 * 16);
   s.cand_id = reinterpret_cast<uint32_t*>(base + stb + (size_t)g.d4 * 16 + (size_t)p.q_smem * 8);
-  s.cand_d = reinterpret_cast<float*>(s.cand_id + 32);
+  s.cand_d = reinterpret_cast<float*>(s.cand_id + 64);
   Stage stg;
   stg.buf = stb ? reinterpret_cast<uint4*>(base) : nullptr;
-  stg.bar = reinterpret_cast<uint64_t*>(s.cand_d + 32);
+  stg.bar = reinterpret_cast<uint64_t*>(s.cand_d + 64);
   stg.phase = 0;
   if (lane == 0) mbar_init(stg.bar, 1);
   __syncwarp();
@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
         pivot = new_pivot;  // hnsw.rs:1526-1528
       }
       // ---- layer-0 (lowest populated layer) search, hnsw.rs:1531-1542
-      search_layer<Op, CH, U, Queue>(g, s, stg, vis, Q, pivot, p.ef, p.layer0, st, overflow);
+      search_layer<Op, CH, U, Queue>(g, s, stg, vis, Q, pivot, p.ef, p.layer0, st, overflow,
+                                     /*speculate=*/p.nq - qi <= p.spec_tail);
       count = min(p.k, min(p.ef, Q.n));  // hnsw.rs:1547
     }
     if (overflow) {

@@ -93,6 +93,7 @@ struct Node {
 
 struct Counters {
   std::atomic<uint64_t> evals{0}, expansions{0}, adj_read{0}, queries{0};
+  std::atomic<uint64_t> spec_ok{0}, spec_total{0};  // study: how often the 2nd-nearest candidate is expanded next
 };
 
 typedef int (*filter_fn_t)(uint64_t origin_id, void* ctx);
@@ -191,7 +192,8 @@ class Index {
     std::vector<uint32_t> stamp;
     uint32_t epoch = 0;
     std::vector<Edge> list;
-    uint64_t evals = 0, expansions = 0, adj_read = 0;
+    uint64_t evals = 0, expansions = 0, adj_read = 0, spec_ok = 0, spec_total = 0;
+    int64_t predicted = -1;
     void begin(size_t n) {
       if (stamp.size() < n) stamp.resize(n + n / 2 + 1024, 0);
       if (++epoch == 0) { std::fill(stamp.begin(), stamp.end(), 0); epoch = 1; }
@@ -217,8 +219,11 @@ class Index {
     C.push(Item{-d0, ep});  // 960-963
     W.push(Item{d0, ep});   // 964-967  (unfiltered)
     const bool has_filter = filter && filter->active;
+    sc.predicted = -1;
     while (!C.empty()) {  // 969
       Item c = C.pop();   // 971
+      if (sc.predicted >= 0) { sc.spec_total++; if ((int64_t)c.id == sc.predicted) sc.spec_ok++; }
+      sc.predicted = C.empty() ? -1 : (int64_t)C.peek().id;  // nearest remaining candidate BEFORE c's neighbours are seen
       // 973 unwraps W.peek(): the reference would PANIC on an empty W here (reachable only with a filter, ef == 1 and
       // an entry point that fails it); the restatement and the engine return the empty W instead.
       if (W.empty()) return W;
@@ -305,7 +310,8 @@ class Index {
 
   void flush(Scratch& sc, uint64_t nq) {
     cnt.evals += sc.evals; cnt.expansions += sc.expansions; cnt.adj_read += sc.adj_read; cnt.queries += nq;
-    sc.evals = sc.expansions = sc.adj_read = 0;
+    cnt.spec_ok += sc.spec_ok; cnt.spec_total += sc.spec_total;
+    sc.evals = sc.expansions = sc.adj_read = sc.spec_ok = sc.spec_total = 0;
   }
 
   // parallel_search: answers in INPUT order whatever the completion order (hnsw.rs:1622-1633)
@@ -684,6 +690,12 @@ void oracle_search_batch(void* hv, const void* qs, uint64_t nq, uint64_t k, uint
   f.ctx = ctx;
   DISPATCH(h, do_search_batch(ix, qs, nq, k, ef, use_filter ? &f : nullptr, nthreads, out_origin, out_dist,
                               out_internal, out_pid, counts));
+}
+
+uint64_t oracle_spec_counters(void* hv, uint64_t* out2) {
+  OracleHandle* h = (OracleHandle*)hv;
+  DISPATCH(h, { out2[0] = ix->cnt.spec_ok; out2[1] = ix->cnt.spec_total; });
+  return 0;
 }
 
 // evals, expansions, adjacency ids read, queries; reset when `reset` != 0

@@ -285,7 +285,7 @@ def run_ours(a, rank, world, local_rank):
     h.set_stream(None)
 
     def step_e2e(b):
-        res = h.search_flat(qh_np[b % NB], a.k, a.ef)
+        res = h.search_flat(qh_np[b % NB], a.k, a.ef, with_internal=False, with_pid=False)   # ids + distances + counts
         if multi:   # answers to rank 0 (host side, gloo)
             t = torch.from_numpy(res[0].view(np.int64))   # gloo has no uint64
             gl = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None

@@ -466,9 +466,11 @@ int hnsw_b200_search_flat(const void* h, const void* queries, uint64_t nq, uint6
     if (r) return r;
     fb = bits.data();
   }
-  std::vector<NeighbourOut> tmp(nq * knbn);
-  int r = pass(ix, ix->search_host(queries, nullptr, nq, (int)dim, knbn, ef_search, fb, tmp.data(), out_counts));
+  const NeighbourOut* tmp = nullptr;
+  const int32_t* cnts = nullptr;
+  int r = pass(ix, ix->search_host_staged(queries, nullptr, nq, (int)dim, knbn, ef_search, fb, &tmp, &cnts));
   if (r) return r;
+  memcpy(out_counts, cnts, nq * sizeof(int32_t));
   for (uint64_t i = 0; i < nq; ++i)
     for (uint64_t j = 0; j < knbn; ++j) {
       const uint64_t o = i * knbn + j;

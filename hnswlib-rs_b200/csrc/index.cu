@@ -89,6 +89,7 @@ Index::~Index() {
   cudaFree(d_vis_tab_); cudaFree(d_vis_epoch_); cudaFree(d_counter_); cudaFree(d_status_); cudaFree(d_stats_);
   cudaFree(d_q_); cudaFree(d_out_); cudaFree(d_cnt_); cudaFree(d_fbits_); cudaFree(d_mask_); cudaFree(d_cbuf_);
   if (h_pin_) cudaFreeHost(h_pin_);
+  if (h_res_) cudaFreeHost(h_res_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   if (own_stream_) cudaStreamDestroy(own_stream_);
@@ -543,8 +544,17 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
   p.cbuf = nullptr;
   p.ccap = 0;
   int bps = 0;
-  if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, 0, smem, stream_, true, &bps));
-  else HB_CUDA(launch_search(p, metric, dtype, 0, smem, stream_, true, &bps));
+  {
+    const auto key = std::make_tuple((int)filtered, p.q_kind, p.g.d4, smem);
+    auto it = occ_cache_.find(key);
+    if (it != occ_cache_.end()) {
+      bps = it->second;
+    } else {
+      if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, 0, smem, stream_, true, &bps));
+      else HB_CUDA(launch_search(p, metric, dtype, 0, smem, stream_, true, &bps));
+      occ_cache_[key] = bps;
+    }
+  }
   if (bps < 1) return fail("search kernel does not fit on an SM");
   if (const char* e = getenv("HNSW_B200_SEARCH_CTAS")) bps = std::max(1, std::min(bps, atoi(e)));  // tuning knob
   int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (nq + wpb - 1) / wpb);
@@ -588,20 +598,35 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
   return 0;
 }
 
-int Index::search_host(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
-                       const uint32_t* filter_bits_host, NeighbourOut* out, int32_t* counts) {
+int Index::search_host_staged(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
+                              const uint32_t* filter_bits_host, const NeighbourOut** out, const int32_t** counts) {
+  *out = nullptr;
+  *counts = nullptr;
   if (nq == 0) return 0;
   HB_CUDA(cudaSetDevice(device));
   if (dim != 0 && d != dim) return fail("query length differs from the index dimension");
-  if (dim == 0) {
-    for (size_t i = 0; i < nq; ++i) counts[i] = 0;
+  int r;
+  const size_t out_bytes = nq * k * sizeof(NeighbourOut), cnt_bytes = nq * sizeof(int32_t);
+  if (h_res_bytes_ < out_bytes + cnt_bytes + 16) {
+    if (h_res_) cudaFreeHost(h_res_);
+    h_res_ = nullptr;
+    h_res_bytes_ = 0;
+    HB_CUDA(cudaMallocHost(&h_res_, out_bytes + cnt_bytes + 16));
+    h_res_bytes_ = out_bytes + cnt_bytes + 16;
+  }
+  NeighbourOut* hout = (NeighbourOut*)h_res_;
+  int32_t* hcnt = (int32_t*)((char*)h_res_ + out_bytes);
+  int32_t* hstatus = hcnt + nq;
+  *out = hout;
+  *counts = hcnt;
+  if (dim == 0) {  // empty index: every answer is empty (hnsw.rs:1498-1503)
+    for (size_t i = 0; i < nq; ++i) hcnt[i] = 0;
     return 0;
   }
-  int r;
   const size_t qbytes = nq * (size_t)dim * es;
   if ((r = ensure_scratch(&d_q_, &d_q_bytes_, qbytes))) return r;
-  if ((r = ensure_scratch(&d_out_, &d_out_bytes_, nq * k * sizeof(NeighbourOut)))) return r;
-  if ((r = ensure_scratch(&d_cnt_, &d_cnt_bytes_, nq * sizeof(int32_t)))) return r;
+  if ((r = ensure_scratch(&d_out_, &d_out_bytes_, out_bytes))) return r;
+  if ((r = ensure_scratch(&d_cnt_, &d_cnt_bytes_, cnt_bytes))) return r;
   if (rows) {
     if (h_pin_bytes_ < qbytes) {
       if (h_pin_) cudaFreeHost(h_pin_);
@@ -623,10 +648,29 @@ int Index::search_host(const void* queries, const void* const* rows, size_t nq, 
     HB_CUDA(cudaMemcpyAsync(d_fbits_, filter_bits_host, fb, cudaMemcpyHostToDevice, stream_));
     dfb = (const uint32_t*)d_fbits_;
   }
-  if ((r = search_device(d_q_, nq, k, ef, dfb, (NeighbourOut*)d_out_, (int32_t*)d_cnt_, true, nullptr))) return r;
-  HB_CUDA(cudaMemcpyAsync(out, d_out_, nq * k * sizeof(NeighbourOut), cudaMemcpyDeviceToHost, stream_));
-  HB_CUDA(cudaMemcpyAsync(counts, d_cnt_, nq * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-  HB_CUDA(cudaStreamSynchronize(stream_));
+  // one enqueue (H2D, kernel, D2H of answers + status), one synchronisation; the slow path (a visited table
+  // overflowed: grow and re-run) is taken only when the status says so
+  for (int pass = 0; pass < 2; ++pass) {
+    if ((r = search_device(d_q_, nq, k, ef, dfb, (NeighbourOut*)d_out_, (int32_t*)d_cnt_, pass == 1, nullptr))) return r;
+    HB_CUDA(cudaMemcpyAsync(hout, d_out_, out_bytes, cudaMemcpyDeviceToHost, stream_));
+    HB_CUDA(cudaMemcpyAsync(hcnt, d_cnt_, cnt_bytes, cudaMemcpyDeviceToHost, stream_));
+    HB_CUDA(cudaMemcpyAsync(hstatus, d_status_, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    HB_CUDA(cudaStreamSynchronize(stream_));
+    if (*hstatus == 0) break;
+    if (pass == 1) return fail("visited table overflow persists");
+    HB_CUDA(cudaMemsetAsync(d_status_, 0, sizeof(int), stream_));
+  }
+  return 0;
+}
+
+int Index::search_host(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
+                       const uint32_t* filter_bits_host, NeighbourOut* out, int32_t* counts) {
+  const NeighbourOut* so;
+  const int32_t* sc;
+  int r = search_host_staged(queries, rows, nq, d, k, ef, filter_bits_host, &so, &sc);
+  if (r || nq == 0) return r;
+  memcpy(counts, sc, nq * sizeof(int32_t));
+  if (dim != 0) memcpy(out, so, nq * k * sizeof(NeighbourOut));
   return 0;
 }
 

@@ -7,7 +7,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -81,6 +83,9 @@ class Index {
   // host queries (flat or row pointers); results to host NeighbourOut[nq][k] + counts
   int search_host(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
                   const uint32_t* filter_bits_host, NeighbourOut* out, int32_t* counts);
+  // same, answers left in the index's pinned staging buffers (valid until the next call on this index)
+  int search_host_staged(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
+                         const uint32_t* filter_bits_host, const NeighbourOut** out, const int32_t** counts);
   int search_device(const void* d_queries, size_t nq, size_t k, size_t ef, const uint32_t* d_filter_bits,
                     NeighbourOut* d_out, int32_t* d_counts, bool sync, float* kernel_ms);
   // filter materialisation: bit per internal id from a sorted origin-id list or a callback
@@ -155,6 +160,9 @@ class Index {
   // staging
   void* h_pin_ = nullptr;
   size_t h_pin_bytes_ = 0;
+  void* h_res_ = nullptr;  // pinned result staging: NeighbourOut[nq*k], int32 counts[nq], int32 status
+  size_t h_res_bytes_ = 0;
+  std::map<std::tuple<int, int, int, size_t>, int> occ_cache_;  // (filtered, queue kind, d4, smem) -> CTAs/SM
   void* d_q_ = nullptr;
   size_t d_q_bytes_ = 0;
   void* d_out_ = nullptr;

@@ -292,15 +292,16 @@ class Hnsw:
 
     parallel_search_neighbours = parallel_search  # AnnT::parallel_search_neighbours
 
-    def search_flat(self, queries, knbn, ef, filter=None):
-        """Extension: flat batch.  Returns (origin u64[nq,k], dist f32[nq,k], internal u32[nq,k], pid i32[nq,k,2], counts)."""
+    def search_flat(self, queries, knbn, ef, filter=None, with_internal=True, with_pid=True):
+        """Extension: flat batch.  Returns (origin u64[nq,k], dist f32[nq,k], internal u32[nq,k] | None,
+        pid i32[nq,k,2] | None, counts)."""
         q = np.ascontiguousarray(queries, self.dtype)
         nq, d = q.shape
         o = np.empty((nq, knbn), np.uint64)
         ds = np.empty((nq, knbn), np.float32)
-        it = np.empty((nq, knbn), np.uint32)
-        pid = np.empty((nq, knbn, 2), np.int32)
-        cnt = np.zeros(nq, np.int32)
+        it = np.empty((nq, knbn), np.uint32) if with_internal else None
+        pid = np.empty((nq, knbn, 2), np.int32) if with_pid else None
+        cnt = np.empty(nq, np.int32)
         mode, fids, nf, cb = 0, None, 0, FILTER_FN(0)
         if filter is not None:
             if callable(filter):

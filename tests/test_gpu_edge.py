@@ -1,0 +1,116 @@
+"""GPU edge cases: long neighbour lists (2M > 32: multi-chunk expansion), ef_construction above the chunked-queue
+limit (generic queue in the insert kernel), capacity growth across many insert calls, tiny / odd shapes, host
+threads sharing one index, error paths.  All checked against the oracle."""
+import threading
+
+import numpy as np
+import pytest
+
+from util import csr_lists
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,efc,d,metric", [(40, 120, 16, "DistL2"), (32, 400, 10, "DistL1"), (129, 300, 8, "DistL2")])
+def test_long_lists_and_big_ef_construction(pkg, po, M, efc, d, metric):
+    """tests/serpar.rs shape (M=32, ef_c=400) and lists longer than one 32-lane chunk (2M = 80, 258)."""
+    n = 1200
+    X = pkg.datagen.uniform(n, d, 31)
+    o = po.Oracle(M, n, 16, efc, metric, d, mode=po.MODE_DET, order=po.ORDER_GPU)
+    levels = o.draw_levels(n)
+    o.insert_batch(X, levels=levels)
+    h = pkg.Hnsw(M, n, 16, efc, metric)
+    h.set_insert_batching(1 << 30, 1)
+    h.insert_flat(X, levels=levels)
+    goff, gids, gds = h.export_layer(0)
+    ooff, oids, ods = o.export_layer(0)
+    assert np.array_equal(goff, ooff) and np.array_equal(gids, oids)
+    assert np.array_equal(gds.view(np.uint32), ods.view(np.uint32))
+    Q = pkg.datagen.uniform(100, d, 32)
+    for k, ef in ((10, 48), (20, 300)):
+        a, b = o.search_batch(Q, k, ef), h.search_flat(Q, k, ef)
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+def test_incremental_inserts_and_capacity_growth(pkg, po):
+    """max_elements is only a hint (hnsw.rs:452-461): 5000 points into an index created for 16, in uneven calls mixing
+    insert_f32, parallel_insert_f32 and the flat call; graph == oracle serial build."""
+    n, d, M, efc = 5000, 12, 8, 40
+    X = pkg.datagen.uniform(n, d, 41)
+    o = po.Oracle(M, 16, 16, efc, "DistL2", d, mode=po.MODE_DET, order=po.ORDER_GPU)
+    levels = o.draw_levels(n)
+    o.insert_batch(X, levels=levels)
+    h = pkg.Hnsw(M, 16, 16, efc, "DistL2")
+    h.set_insert_batching(1 << 30, 1)
+    pos = 0
+    for sz in (1, 1, 3, 50, 700, 1, 2000, 2244):
+        h.insert_flat(X[pos:pos + sz], ids=np.arange(pos, pos + sz), levels=levels[pos:pos + sz])
+        pos += sz
+    assert pos == n and h.get_nb_point() == n
+    goff, gids, _ = h.export_layer(0)
+    ooff, oids, _ = o.export_layer(0)
+    assert np.array_equal(goff, ooff) and np.array_equal(gids, oids)
+    for layer in (1, 2):
+        gl = csr_lists(*h.export_layer(layer)[:2])
+        ol = csr_lists(*o.export_layer(layer)[:2])
+        lv = o.export_points()[0]
+        assert all(gl[p] == ol[p] for p in range(n) if lv[p] >= layer)
+
+
+def test_tiny_and_odd_shapes(pkg, po):
+    # one point, k larger than the index
+    h = pkg.Hnsw(4, 10, 16, 8, "DistL2")
+    h.insert((np.array([1.0, 2.0, 3.0], np.float32), 9))
+    r = h.search(np.array([1.0, 2.0, 3.0], np.float32), 5, 3)
+    assert len(r) == 1 and r[0].d_id == 9 and r[0].distance == 0.0
+    # u8 vectors of 3 bytes (row tail handled byte-wise), d = 1
+    for dt, d in ((np.uint8, 3), (np.float32, 1), (np.uint16, 5)):
+        rng = np.random.default_rng(1)
+        X = rng.integers(0, 50, (300, d)).astype(dt)
+        metric = "DistL1"
+        o = po.Oracle(6, 300, 16, 20, metric, d, dtype=dt, mode=po.MODE_DET, order=po.ORDER_GPU)
+        lv = o.draw_levels(300)
+        o.insert_batch(X, levels=lv)
+        g = pkg.Hnsw(6, 300, 16, 20, metric, dtype=dt)
+        g.set_insert_batching(1 << 30, 1)
+        g.insert_flat(X, levels=lv)
+        a, b = o.search_batch(X[:40], 4, 16), g.search_flat(X[:40], 4, 16)
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+def test_many_host_threads_one_index(pkg, po):
+    """search* take &self and may be called from many host threads (hnsw.rs:830-833)"""
+    X = pkg.datagen.uniform(3000, 16, 51)
+    h = pkg.Hnsw(12, 3000, 16, 64, "DistL2")
+    h.insert_flat(X)
+    Q = pkg.datagen.uniform(64, 16, 52)
+    want = h.search_flat(Q, 5, 32)
+    out, errs = {}, []
+
+    def work(t):
+        try:
+            for _ in range(5):
+                out[t] = h.search_flat(Q, 5, 32)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    for t in range(8):
+        assert np.array_equal(out[t][0], want[0]) and np.array_equal(out[t][1], want[1])
+
+
+def test_error_paths_are_loud(pkg):
+    h = pkg.Hnsw(8, 100, 16, 20, "DistL2")
+    h.insert((np.zeros(6, np.float32), 0))
+    with pytest.raises(pkg.HnswError):          # dimension mismatch is refused (the flat store needs one dimension)
+        h.insert((np.zeros(7, np.float32), 1))
+    with pytest.raises(pkg.HnswError):
+        h.search_flat(np.zeros((2, 9), np.float32), 3, 8)
+    with pytest.raises(pkg.HnswError):          # Jaccard is not defined for i32 upstream either (libext.rs:779-810)
+        pkg.Hnsw(8, 10, 16, 20, "DistJaccard", dtype=np.int32)
+    with pytest.raises(pkg.HnswError):
+        pkg.Hnsw(1, 10, 16, 20, "DistL2")      # ln(1) = 0 breaks the level law
+    with pytest.raises(pkg.HnswError):
+        h.modify_level_scale(0.5)               # only before the first insert (hnsw.rs:881-888)

@@ -664,6 +664,7 @@ struct SortedQueue {
       __syncwarp();
       top = lo - 1;
     }
+    __syncwarp();  // reads of the queue by other lanes (accepts, rank) happen-before the write below
     if (lane == 0) w[pos] = key;
     __syncwarp();
     n = new_n;
@@ -692,6 +693,7 @@ struct SmemQueueN {
   __device__ __forceinline__ uint64_t get(int i) const { return w[i]; }
   __device__ __forceinline__ uint64_t local(int i) const { return w[i]; }
   __device__ __forceinline__ void mark_expanded(int i) {
+    __syncwarp();  // other lanes' reads of the queue (scans, get) happen-before this write (racecheck: WAR hazard)
     if (lane_id() == 0) w[i] |= 1ull;
     __syncwarp();
   }

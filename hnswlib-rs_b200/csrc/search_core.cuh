@@ -31,6 +31,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
   const int lane = lane_id();
   const uint4* vec4 = reinterpret_cast<const uint4*>(g.vec);
   vis.begin();
+  __syncwarp();  // earlier reads of cand_id (descent, previous layer) happen-before the write below
   if (lane == 0) s.cand_id[0] = ep;
   __syncwarp();
   warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, 1, s.cand_d);  // hnsw.rs:952

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) dist_batch_kernel(AuxParams p) {
       __syncwarp();
       warp_dists<Op, CH, U>(vec4, p.g.d4, p.g.dim, q4, cid, cnt, cd);
       __syncwarp();
-      if (lane < cnt) p.out[(size_t)qi * p.m + b + lane] = cd[lane];
+      if (lane < cnt) p.out[(size_t)qi * p.m + b + lane] = Op::post(cd[lane]);
       __syncwarp();
     }
   }
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) bruteforce_kernel(AuxParams p) {
       __syncwarp();
       warp_dists<Op, CH, U>(vec4, p.g.d4, p.g.dim, q4, cid, cnt, cd);
       __syncwarp();
-      const uint64_t key = lane < cnt ? make_key(cd[lane], b + lane) : ~0ull;
+      const uint64_t key = lane < cnt ? make_key(Op::post(cd[lane]), b + lane) : ~0ull;
       unsigned acc = __ballot_sync(FULL, lane < cnt && Q.accepts(key));
       while (acc) {
         const int j = __ffs(acc) - 1;

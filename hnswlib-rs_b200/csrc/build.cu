@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
     __syncwarp();
     warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, 1, s.cand_d);
     __syncwarp();
-    float dist_to_entry = s.cand_d[0];
+    float dist_to_entry = Op::post(s.cand_d[0]);
     // ---- layers above the new point's level: ef = 1 (hnsw.rs:1114-1155).  The reference also pushes
     // the result into new_point.neighbours[l] for l above its level (1140-1144); that list can never
     // be traversed (DESIGN.md "lists above a point's level") and is not materialised.
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
             dists_from_point<Op, CH, U>(g, qe4, e, sel_id, cnt, tmp);
             st.evals += cnt;
             for (int b = 0; b < cnt; b += 32) {
-              const bool bad = (b + lane < cnt) && (tmp[b + lane] <= de);
+              const bool bad = (b + lane < cnt) && (Op::post(tmp[b + lane]) <= de);
               if (__any_sync(FULL, bad)) {
                 keep = false;
                 break;

@@ -86,7 +86,9 @@ struct OpL2 {
     a = __fmaf_rn(df, df, a);
   }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
-  static __device__ __forceinline__ float finish(acc_t a, int) { return __fsqrt_rn(a); }
+  // finish() runs once per row pass in every lane, post() once per candidate: the square root is deferred to post()
+  static __device__ __forceinline__ float finish(acc_t a, int) { return a; }
+  static __device__ __forceinline__ float post(float v) { return __fsqrt_rn(v); }
   static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
     step(a, __uint_as_float(q.x), __uint_as_float(x.x));
     step(a, __uint_as_float(q.y), __uint_as_float(x.y));
@@ -100,6 +102,7 @@ struct OpL1 {
   static __device__ __forceinline__ void step(acc_t& a, float q, float x) { a = __fadd_rn(a, fabsf(__fsub_rn(q, x))); }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
   static __device__ __forceinline__ float finish(acc_t a, int) { return a; }
+  static __device__ __forceinline__ float post(float v) { return v; }
   static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
     step(a, __uint_as_float(q.x), __uint_as_float(x.x));
     step(a, __uint_as_float(q.y), __uint_as_float(x.y));
@@ -113,6 +116,7 @@ struct OpDot {
   static __device__ __forceinline__ void step(acc_t& a, float q, float x) { a = __fmaf_rn(q, x, a); }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
   static __device__ __forceinline__ float finish(acc_t a, int) { return fmaxf(__fsub_rn(1.0f, a), 0.f); }
+  static __device__ __forceinline__ float post(float v) { return v; }
   static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
     step(a, __uint_as_float(q.x), __uint_as_float(x.x));
     step(a, __uint_as_float(q.y), __uint_as_float(x.y));
@@ -146,6 +150,7 @@ struct OpCosine {  // f64 accumulation like anndists DistCosine
     }
     return 0.f;
   }
+  static __device__ __forceinline__ float post(float v) { return v; }
   static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
     step(a, __uint_as_float(q.x), __uint_as_float(x.x));
     step(a, __uint_as_float(q.y), __uint_as_float(x.y));
@@ -159,6 +164,7 @@ struct OpHellinger {
   static __device__ __forceinline__ void step(acc_t& a, float q, float x) { a = __fadd_rn(a, __fsqrt_rn(__fmul_rn(q, x))); }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
   static __device__ __forceinline__ float finish(acc_t a, int) { return __fsqrt_rn(fmaxf(__fsub_rn(1.0f, a), 0.f)); }
+  static __device__ __forceinline__ float post(float v) { return v; }
   static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
     step(a, __uint_as_float(q.x), __uint_as_float(x.x));
     step(a, __uint_as_float(q.y), __uint_as_float(x.y));
@@ -175,6 +181,7 @@ struct OpJeffreys {
   }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
   static __device__ __forceinline__ float finish(acc_t a, int) { return a; }
+  static __device__ __forceinline__ float post(float v) { return v; }
   static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
     step(a, __uint_as_float(q.x), __uint_as_float(x.x));
     step(a, __uint_as_float(q.y), __uint_as_float(x.y));
@@ -194,6 +201,7 @@ struct OpJS {
   }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
   static __device__ __forceinline__ float finish(acc_t a, int) { return __fsqrt_rn(fmaxf(__fmul_rn(0.5f, a), 0.f)); }
+  static __device__ __forceinline__ float post(float v) { return v; }
   static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
     step(a, __uint_as_float(q.x), __uint_as_float(x.x));
     step(a, __uint_as_float(q.y), __uint_as_float(x.y));
@@ -244,6 +252,7 @@ struct OpCast {
   }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return FOp::comb(a, off); }
   static __device__ __forceinline__ float finish(acc_t a, int d) { return FOp::finish(a, d); }
+  static __device__ __forceinline__ float post(float v) { return FOp::post(v); }
 };
 
 template <class T>
@@ -260,6 +269,7 @@ struct OpHamming {  // DistHamming: #{a_i != b_i} / len
   }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return a + __shfl_xor_sync(FULL, a, off); }
   static __device__ __forceinline__ float finish(acc_t a, int d) { return __fdiv_rn((float)a, (float)d); }
+  static __device__ __forceinline__ float post(float v) { return v; }
 };
 
 struct MinMax64 {
@@ -294,6 +304,7 @@ struct OpJaccard {  // weighted Jaccard: 1 - sum min / sum max, integer sums, f6
     if (a.mx == 0ull) return 0.f;
     return (float)__dsub_rn(1.0, __ddiv_rn((double)a.mn, (double)a.mx));
   }
+  static __device__ __forceinline__ float post(float v) { return v; }
 };
 
 template <class Op>
@@ -640,6 +651,11 @@ struct SortedQueue {
     }
     return -1;
   }
+  __device__ __forceinline__ void next3(int from, int& a, int& b, int& c) const {
+    a = next_unexpanded(from);
+    b = a >= 0 ? next_unexpanded(a + 1) : -1;
+    c = b >= 0 ? next_unexpanded(b + 1) : -1;
+  }
   __device__ __forceinline__ bool accepts(uint64_t key) const { return n < cap || key < (w[n - 1] & ~1ull); }
   // insert key (expanded bit clear) keeping order; drops the largest entry when full. Caller checked accepts().
   __device__ __forceinline__ void insert(uint64_t key) {
@@ -712,6 +728,29 @@ struct SmemQueueN {
       if (m) return 32 * c + __ffs(m) - 1;
     }
     return -1;
+  }
+  // first three unexpanded indices at or after `from` in one pass over the queue (-1 when absent)
+  __device__ __forceinline__ void next3(int from, int& a, int& b, int& c) const {
+    const int lane = lane_id();
+    unsigned m[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int i = 32 * ch + lane;
+      m[ch] = __ballot_sync(FULL, ((w[i] & 1ull) == 0ull) && i >= from);
+    }
+    int out[3] = {-1, -1, -1};
+    int k = 0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      unsigned mm = m[ch];
+      while (mm && k < 3) {
+        out[k++] = 32 * ch + __ffs(mm) - 1;
+        mm &= mm - 1;
+      }
+    }
+    a = out[0];
+    b = out[1];
+    c = out[2];
   }
   // when the queue is not full its last slot holds ~0, so one comparison covers both cases
   __device__ __forceinline__ bool accepts(uint64_t key) const { return key < (w[cap - 1] & ~1ull); }
@@ -792,6 +831,11 @@ struct RegQueue {
       if (m) return 32 * s + __ffs(m) - 1;
     }
     return -1;
+  }
+  __device__ __forceinline__ void next3(int from, int& a, int& b, int& c) const {
+    a = next_unexpanded(from);
+    b = a >= 0 ? next_unexpanded(a + 1) : -1;
+    c = b >= 0 ? next_unexpanded(b + 1) : -1;
   }
   __device__ __forceinline__ bool accepts(uint64_t key) const { return n < cap || key < fkey; }
   __device__ __forceinline__ void insert(uint64_t key) {

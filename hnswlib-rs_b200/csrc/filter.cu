@@ -32,7 +32,7 @@ __device__ __forceinline__ void search_layer_filtered(const GraphView& g, const 
   warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, 1, s.cand_d);  // hnsw.rs:952
   __syncwarp();
   st.evals += 1;
-  const float d0 = s.cand_d[0];
+  const float d0 = Op::post(s.cand_d[0]);
   vis.test_and_set(ep, lane == 0);
   W.reset(s.wbuf, ef);
   if (lane == 0) {
@@ -110,7 +110,7 @@ __device__ __forceinline__ void search_layer_filtered(const GraphView& g, const 
         __syncwarp();
         st.evals += cnt;
         const uint32_t my_id = lane < cnt ? s.cand_id[lane] : 0u;
-        const uint64_t key = lane < cnt ? make_key(s.cand_d[lane], my_id) : ~0ull;
+        const uint64_t key = lane < cnt ? make_key(Op::post(s.cand_d[lane]), my_id) : ~0ull;
         const bool my_pass = lane < cnt && filter_pass(fbits, my_id);
         const unsigned passmask = __ballot_sync(FULL, my_pass);
         for (int j = 0; j < cnt; ++j) {  // strictly in list order: the accept rule sees the W of that moment
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_filter_kernel(SearchPar
       warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, 1, s.cand_d);
       __syncwarp();
       st.evals += 1;
-      float best = s.cand_d[0];
+      float best = Op::post(s.cand_d[0]);
       for (int layer = g.entry_level; layer >= 1; --layer) {
         int cap;
         const uint32_t* ids = list_ids(g, pivot, layer, cap);
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_filter_kernel(SearchPar
             __syncwarp();
             st.evals += cnt;
             st.adj += cnt;
-            uint64_t key = lane < cnt ? (((uint64_t)__float_as_uint(s.cand_d[lane]) << 32) | (uint32_t)lane) : ~0ull;
+            uint64_t key = lane < cnt ? (((uint64_t)__float_as_uint(Op::post(s.cand_d[lane])) << 32) | (uint32_t)lane) : ~0ull;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
               uint64_t other = __shfl_xor_sync(FULL, key, o);

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
       warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, 1, s.cand_d);  // hnsw.rs:1506
       __syncwarp();
       st.evals += 1;
-      float best = s.cand_d[0];
+      float best = Op::post(s.cand_d[0]);
       for (int layer = g.entry_level; layer >= 1; --layer) {
         int cap;
         const uint32_t* ids = list_ids(g, pivot, layer, cap);
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
             st.evals += cnt;
             st.adj += cnt;
             // strict `<` scanned in list order == first minimum of the list, if below `best`
-            uint64_t key = lane < cnt ? (((uint64_t)__float_as_uint(s.cand_d[lane]) << 32) | (uint32_t)lane) : ~0ull;
+            uint64_t key = lane < cnt ? (((uint64_t)__float_as_uint(Op::post(s.cand_d[lane])) << 32) | (uint32_t)lane) : ~0ull;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
               uint64_t other = __shfl_xor_sync(FULL, key, o);

@@ -37,7 +37,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
   warp_dists<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, 1, s.cand_d);  // hnsw.rs:952
   __syncwarp();
   st.evals += 1;
-  const float d0 = s.cand_d[0];
+  const float d0 = Op::post(s.cand_d[0]);
   vis.test_and_set(ep, lane == 0);  // hnsw.rs:955-956
   Q.reset(s.wbuf, ef);
   Q.push_first(make_key(d0, ep));  // hnsw.rs:958-967 (ep enters W and C)
@@ -52,23 +52,24 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
     // study).  Its neighbour rows are fetched together with c's; its results are committed only if it really is the
     // next pick once c's neighbours are in the queue, otherwise they are dropped and no state has changed.
     // At full load the extra probe and the 12 % wasted rows cost more than the shorter chain gains (measured).
+    // the next unexpanded entries after idx, found in one pass: speculation target (when enabled) and L2 prefetch
+    int n1, n2, n3;
+    Q.next3(idx + 1, n1, n2, n3);
     int i2 = -1;
     uint32_t c2 = INVALID_ID;
     const uint32_t* ids2 = nullptr;
-    if (speculate && cap <= 32 && ef > 1) {
-      i2 = Q.next_unexpanded(idx + 1);
-      if (i2 >= 0) {
-        c2 = key_id(Q.get(i2));
-        int cap2;
-        ids2 = list_ids(g, c2, layer, cap2);
-        if (!ids2) c2 = INVALID_ID;
-      }
+    if (speculate && cap <= 32 && ef > 1 && n1 >= 0) {
+      i2 = n1;
+      c2 = key_id(Q.get(i2));
+      int cap2;
+      ids2 = list_ids(g, c2, layer, cap2);
+      if (!ids2) c2 = INVALID_ID;
     }
     Q.mark_expanded(idx);
     st.expansions += 1;
     {  // pull the adjacency rows of the following candidates towards L2
-      const int i3 = Q.next_unexpanded((i2 >= 0 ? i2 : idx) + 1);
-      const int i4 = i3 >= 0 ? Q.next_unexpanded(i3 + 1) : -1;
+      const int i3 = i2 >= 0 ? n2 : n1;
+      const int i4 = i2 >= 0 ? n3 : n2;
       const uint32_t c3 = i3 >= 0 ? key_id(Q.get(i3)) : INVALID_ID;
       const uint32_t c4 = i4 >= 0 ? key_id(Q.get(i4)) : INVALID_ID;
       const uint32_t pc = lane == 0 ? c3 : (lane == 1 ? c4 : INVALID_ID);
@@ -99,7 +100,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
       }
       st.evals += cnt;
       {
-        const uint64_t key = lane < cnt ? make_key(s.cand_d[lane], s.cand_id[lane]) : ~0ull;
+        const uint64_t key = lane < cnt ? make_key(Op::post(s.cand_d[lane]), s.cand_id[lane]) : ~0ull;
         unsigned acc = __ballot_sync(FULL, lane < cnt && Q.accepts(key));  // hnsw.rs:1028
         while (acc) {
           const int j = __ffs(acc) - 1;
@@ -116,7 +117,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
           st.adj += __popc(__ballot_sync(FULL, nid2 != INVALID_ID));
           vis.test_and_set(nid2, spec);  // now record them (all fresh by construction)
           st.evals += cnt2;
-          const uint64_t key = lane < cnt2 ? make_key(s.cand_d[cnt + lane], s.cand_id[cnt + lane]) : ~0ull;
+          const uint64_t key = lane < cnt2 ? make_key(Op::post(s.cand_d[cnt + lane]), s.cand_id[cnt + lane]) : ~0ull;
           unsigned acc = __ballot_sync(FULL, lane < cnt2 && Q.accepts(key));
           while (acc) {
             const int j = __ffs(acc) - 1;
@@ -141,7 +142,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
           warp_dists_staged<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, cnt, s.cand_d, stg);  // hnsw.rs:1026
           __syncwarp();
           st.evals += cnt;
-          const uint64_t key = lane < cnt ? make_key(s.cand_d[lane], s.cand_id[lane]) : ~0ull;
+          const uint64_t key = lane < cnt ? make_key(Op::post(s.cand_d[lane]), s.cand_id[lane]) : ~0ull;
           unsigned acc = __ballot_sync(FULL, lane < cnt && Q.accepts(key));  // hnsw.rs:1028
           while (acc) {
             const int j = __ffs(acc) - 1;

@@ -78,57 +78,93 @@ __device__ __forceinline__ const uint32_t* list_ids(const GraphView& g, uint32_t
 // lane g (0..7) of a row group owns float4 chunks g, g+8, g+16, ...; inside a chunk x,y,z,w in that
 // order; fused multiply-add where a product is accumulated; then partials are combined with a
 // 4,2,1 xor butterfly and finished (sqrt / 1-x / ...).  Zero padding adds exact zeros.
+// f32 L2 / L1 / Dot keep two partial sums per lane (elements x,z and y,w of each chunk: packed f32x2 math) that
+// are added before the butterfly; every other op keeps one.
+// packed f32x2 arithmetic (Blackwell FADD2 / FFMA2): two IEEE round-to-nearest operations per instruction
+__device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float fold2(unsigned long long a) {  // lo + hi
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(a));
+  return __fadd_rn(__uint_as_float(lo), __uint_as_float(hi));
+}
+
+// L2 / L1 / Dot accumulate TWO partial sums per lane with packed f32x2 instructions: the low half takes the
+// elements x and z of every 16-byte chunk, the high half y and w; fold() adds the halves before the butterfly.
+// (The scalar step() is the single-accumulator form used for integer element types, OpCast.)
 struct OpL2 {
-  typedef float acc_t;
-  static __device__ __forceinline__ acc_t zero() { return 0.f; }
-  static __device__ __forceinline__ void step(acc_t& a, float q, float x) {
+  typedef unsigned long long acc_t;
+  typedef float red_t;
+  static __device__ __forceinline__ acc_t zero() { return 0ull; }
+  static __device__ __forceinline__ void step(float& a, float q, float x) {
     float df = __fsub_rn(q, x);
     a = __fmaf_rn(df, df, a);
   }
-  static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
-  // finish() runs once per row pass in every lane, post() once per candidate: the square root is deferred to post()
-  static __device__ __forceinline__ float finish(acc_t a, int) { return a; }
-  static __device__ __forceinline__ float post(float v) { return __fsqrt_rn(v); }
   static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
-    step(a, __uint_as_float(q.x), __uint_as_float(x.x));
-    step(a, __uint_as_float(q.y), __uint_as_float(x.y));
-    step(a, __uint_as_float(q.z), __uint_as_float(x.z));
-    step(a, __uint_as_float(q.w), __uint_as_float(x.w));
+    const unsigned long long d01 = sub2(pack2(q.x, q.y), pack2(x.x, x.y));
+    a = fma2(d01, d01, a);
+    const unsigned long long d23 = sub2(pack2(q.z, q.w), pack2(x.z, x.w));
+    a = fma2(d23, d23, a);
   }
+  static __device__ __forceinline__ red_t fold(acc_t a) { return fold2(a); }
+  static __device__ __forceinline__ red_t comb(red_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
+  // finish() runs once per row pass in every lane, post() once per candidate: the square root is deferred to post()
+  static __device__ __forceinline__ float finish(red_t a, int) { return a; }
+  static __device__ __forceinline__ float post(float v) { return __fsqrt_rn(v); }
 };
 struct OpL1 {
-  typedef float acc_t;
-  static __device__ __forceinline__ acc_t zero() { return 0.f; }
-  static __device__ __forceinline__ void step(acc_t& a, float q, float x) { a = __fadd_rn(a, fabsf(__fsub_rn(q, x))); }
-  static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
-  static __device__ __forceinline__ float finish(acc_t a, int) { return a; }
-  static __device__ __forceinline__ float post(float v) { return v; }
+  typedef unsigned long long acc_t;
+  typedef float red_t;
+  static __device__ __forceinline__ acc_t zero() { return 0ull; }
+  static __device__ __forceinline__ void step(float& a, float q, float x) { a = __fadd_rn(a, fabsf(__fsub_rn(q, x))); }
   static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
-    step(a, __uint_as_float(q.x), __uint_as_float(x.x));
-    step(a, __uint_as_float(q.y), __uint_as_float(x.y));
-    step(a, __uint_as_float(q.z), __uint_as_float(x.z));
-    step(a, __uint_as_float(q.w), __uint_as_float(x.w));
+    const unsigned long long absmask = 0x7FFFFFFF7FFFFFFFull;
+    a = add2(a, sub2(pack2(q.x, q.y), pack2(x.x, x.y)) & absmask);
+    a = add2(a, sub2(pack2(q.z, q.w), pack2(x.z, x.w)) & absmask);
   }
+  static __device__ __forceinline__ red_t fold(acc_t a) { return fold2(a); }
+  static __device__ __forceinline__ red_t comb(red_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
+  static __device__ __forceinline__ float finish(red_t a, int) { return a; }
+  static __device__ __forceinline__ float post(float v) { return v; }
 };
 struct OpDot {
-  typedef float acc_t;
-  static __device__ __forceinline__ acc_t zero() { return 0.f; }
-  static __device__ __forceinline__ void step(acc_t& a, float q, float x) { a = __fmaf_rn(q, x, a); }
-  static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
-  static __device__ __forceinline__ float finish(acc_t a, int) { return fmaxf(__fsub_rn(1.0f, a), 0.f); }
-  static __device__ __forceinline__ float post(float v) { return v; }
+  typedef unsigned long long acc_t;
+  typedef float red_t;
+  static __device__ __forceinline__ acc_t zero() { return 0ull; }
   static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
-    step(a, __uint_as_float(q.x), __uint_as_float(x.x));
-    step(a, __uint_as_float(q.y), __uint_as_float(x.y));
-    step(a, __uint_as_float(q.z), __uint_as_float(x.z));
-    step(a, __uint_as_float(q.w), __uint_as_float(x.w));
+    a = fma2(pack2(q.x, q.y), pack2(x.x, x.y), a);
+    a = fma2(pack2(q.z, q.w), pack2(x.z, x.w), a);
   }
+  static __device__ __forceinline__ red_t fold(acc_t a) { return fold2(a); }
+  static __device__ __forceinline__ red_t comb(red_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
+  static __device__ __forceinline__ float finish(red_t a, int) { return fmaxf(__fsub_rn(1.0f, a), 0.f); }
+  static __device__ __forceinline__ float post(float v) { return v; }
 };
 struct Cos3 {
   double ab, aa, bb;
 };
 struct OpCosine {  // f64 accumulation like anndists DistCosine
   typedef Cos3 acc_t;
+  typedef acc_t red_t;
+  static __device__ __forceinline__ red_t fold(acc_t a) { return a; }
   static __device__ __forceinline__ acc_t zero() { return Cos3{0., 0., 0.}; }
   static __device__ __forceinline__ void step(acc_t& a, float q, float x) {
     double dq = (double)q, dx = (double)x;
@@ -160,6 +196,8 @@ struct OpCosine {  // f64 accumulation like anndists DistCosine
 };
 struct OpHellinger {
   typedef float acc_t;
+  typedef acc_t red_t;
+  static __device__ __forceinline__ red_t fold(acc_t a) { return a; }
   static __device__ __forceinline__ acc_t zero() { return 0.f; }
   static __device__ __forceinline__ void step(acc_t& a, float q, float x) { a = __fadd_rn(a, __fsqrt_rn(__fmul_rn(q, x))); }
   static __device__ __forceinline__ acc_t comb(acc_t a, int off) { return __fadd_rn(a, __shfl_xor_sync(FULL, a, off)); }
@@ -174,6 +212,8 @@ struct OpHellinger {
 };
 struct OpJeffreys {
   typedef float acc_t;
+  typedef acc_t red_t;
+  static __device__ __forceinline__ red_t fold(acc_t a) { return a; }
   static __device__ __forceinline__ acc_t zero() { return 0.f; }
   static __device__ __forceinline__ void step(acc_t& a, float q, float x) {
     float qm = fmaxf(q, 1e-30f), xm = fmaxf(x, 1e-30f);
@@ -191,6 +231,8 @@ struct OpJeffreys {
 };
 struct OpJS {
   typedef float acc_t;
+  typedef acc_t red_t;
+  static __device__ __forceinline__ red_t fold(acc_t a) { return a; }
   static __device__ __forceinline__ acc_t zero() { return 0.f; }
   static __device__ __forceinline__ void step(acc_t& a, float q, float x) {
     float m = __fmul_rn(0.5f, __fadd_rn(q, x));
@@ -245,6 +287,8 @@ struct Elems<uint8_t> {
 template <class T, class FOp>  // FOp = OpL1 / OpL2 on the elements cast to f32
 struct OpCast {
   typedef float acc_t;
+  typedef float red_t;
+  static __device__ __forceinline__ red_t fold(acc_t a) { return a; }
   static __device__ __forceinline__ acc_t zero() { return 0.f; }
   static __device__ __forceinline__ void chunk(acc_t& a, const uint4& q, const uint4& x) {
 #pragma unroll
@@ -258,6 +302,8 @@ struct OpCast {
 template <class T>
 struct OpHamming {  // DistHamming: #{a_i != b_i} / len
   typedef uint32_t acc_t;
+  typedef acc_t red_t;
+  static __device__ __forceinline__ red_t fold(acc_t a) { return a; }
   static __device__ __forceinline__ acc_t zero() { return 0u; }
   static __device__ __forceinline__ uint32_t ne(uint32_t a, uint32_t b) {
     if (sizeof(T) == 1) return __popc(__vcmpne4(a, b) & 0x01010101u);
@@ -278,6 +324,8 @@ struct MinMax64 {
 template <class T>
 struct OpJaccard {  // weighted Jaccard: 1 - sum min / sum max, integer sums, f64 division
   typedef MinMax64 acc_t;
+  typedef acc_t red_t;
+  static __device__ __forceinline__ red_t fold(acc_t a) { return a; }
   static __device__ __forceinline__ acc_t zero() { return MinMax64{0ull, 0ull}; }
   static __device__ __forceinline__ void word(acc_t& a, uint32_t q, uint32_t x) {
     if (sizeof(T) == 1) {
@@ -308,7 +356,8 @@ struct OpJaccard {  // weighted Jaccard: 1 - sum min / sum max, integer sums, f6
 };
 
 template <class Op>
-__device__ __forceinline__ float reduce8(typename Op::acc_t a, int dim) {
+__device__ __forceinline__ float reduce8(typename Op::acc_t acc, int dim) {
+  typename Op::red_t a = Op::fold(acc);
   a = Op::comb(a, 4);
   a = Op::comb(a, 2);
   a = Op::comb(a, 1);

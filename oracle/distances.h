@@ -47,6 +47,7 @@ enum SumOrder : int { ORDER_REF = 0, ORDER_GPU = 1 };
 
 // ---------------------------------------------------------------- per-element functors
 struct AccL1 {
+  static constexpr bool packed = true;  // GPU uses packed f32x2 math for this metric on f32 data
   static inline float step(float acc, float a, float b, bool fused) {
     (void)fused;
     return acc + std::fabs(a - b);
@@ -54,6 +55,7 @@ struct AccL1 {
   static inline float finish(float s) { return s; }
 };
 struct AccL2 {
+  static constexpr bool packed = true;  // GPU uses packed f32x2 math for this metric on f32 data
   static inline float step(float acc, float a, float b, bool fused) {
     float df = a - b;
     return fused ? std::fmaf(df, df, acc) : acc + df * df;
@@ -61,6 +63,7 @@ struct AccL2 {
   static inline float finish(float s) { return std::sqrt(s); }
 };
 struct AccDot {
+  static constexpr bool packed = true;  // GPU uses packed f32x2 math for this metric on f32 data
   static inline float step(float acc, float a, float b, bool fused) {
     return fused ? std::fmaf(a, b, acc) : acc + a * b;
   }
@@ -70,6 +73,7 @@ struct AccDot {
   }
 };
 struct AccHellinger {
+  static constexpr bool packed = false;  // GPU uses packed f32x2 math for this metric on f32 data
   static inline float step(float acc, float a, float b, bool fused) {
     (void)fused;
     return acc + std::sqrt(a * b);
@@ -80,6 +84,7 @@ struct AccHellinger {
   }
 };
 struct AccJeffreys {
+  static constexpr bool packed = false;  // GPU uses packed f32x2 math for this metric on f32 data
   static inline float step(float acc, float a, float b, bool fused) {
     (void)fused;
     float am = a > 1e-30f ? a : 1e-30f, bm = b > 1e-30f ? b : 1e-30f;
@@ -88,6 +93,7 @@ struct AccJeffreys {
   static inline float finish(float s) { return s; }
 };
 struct AccJS {
+  static constexpr bool packed = false;  // GPU uses packed f32x2 math for this metric on f32 data
   static inline float step(float acc, float a, float b, bool fused) {
     (void)fused;
     float m = 0.5f * (a + b);
@@ -118,16 +124,21 @@ static inline float accumulate_ref(const T* a, const T* b, size_t d) {
 template <class Acc, class T>
 static inline float accumulate_gpu(const T* a, const T* b, size_t d) {
   // a 16-byte chunk holds EPC elements (4 x f32/i32/u32, 8 x u16, 16 x u8); lane g owns chunks g, g+8, ...
+  // f32 data with a packed-math metric (L1, L2, Dot): TWO partial sums per lane, elements 0,2 of each 4-element
+  // chunk in the first, 1,3 in the second, added once at the end (FADD2/FFMA2 on the GPU).  Otherwise one sum.
   const size_t EPC = 16 / sizeof(T);
+  const bool two = std::is_same<T, float>::value && Acc::packed;
   float p[8];
   for (int g = 0; g < 8; ++g) {
-    float acc = 0.f;
+    float acc0 = 0.f, acc1 = 0.f;
     for (size_t c4 = g; EPC * c4 < d; c4 += 8)
       for (size_t k = 0; k < EPC; ++k) {
         size_t e = EPC * c4 + k;
-        if (e < d) acc = Acc::step(acc, (float)a[e], (float)b[e], true);
+        if (e >= d) continue;
+        if (two && (k & 1)) acc1 = Acc::step(acc1, (float)a[e], (float)b[e], true);
+        else acc0 = Acc::step(acc0, (float)a[e], (float)b[e], true);
       }
-    p[g] = acc;
+    p[g] = two ? acc0 + acc1 : acc0;
   }
   for (int g = 0; g < 4; ++g) p[g] = p[g] + p[g + 4];
   for (int g = 0; g < 2; ++g) p[g] = p[g] + p[g + 2];

@@ -279,6 +279,20 @@ def run_ours(a, rank, world, local_rank):
            for i in range(min(a.steps, 10))]
     kernel_ms = float(np.mean(kms))
 
+    # ---- steady-state reference point (not the metric): one launch of 10x the step's queries, where ramp-up and tail of
+    # the 2-wave step no longer dominate (BASELINE configs[4] runs 125 000 queries per GPU, i.e. in this regime)
+    steady = None
+    if rank == 0 and not multi:
+        nbig = 10 * a.nq
+        qb = torch.from_numpy(pkg.datagen.make(a.data, nbig, a.d, 777)).cuda()
+        ob = torch.empty((nbig, a.k, 16), dtype=torch.uint8, device="cuda")
+        cb = torch.empty((nbig,), dtype=torch.int32, device="cuda")
+        h.search_device(qb.data_ptr(), nbig, a.k, a.ef, ob.data_ptr(), cb.data_ptr(), sync=True)
+        ms_big = min(h.search_device(qb.data_ptr(), nbig, a.k, a.ef, ob.data_ptr(), cb.data_ptr(), sync=True) for _ in range(3))
+        steady = {"queries_per_launch": nbig, "kernel_ms": ms_big, "queries_per_s": nbig / ms_big * 1e3,
+                  "algorithmic_GBps": bytes_per_query * nbig / ms_big / 1e6}
+        del qb, ob, cb
+
     # ---- end to end through the C-ABI call with host buffers (H2D + kernel + D2H per step)
     gloo = dist.new_group(backend="gloo") if multi else None
     qh_np = [q.numpy() for q in q_host]
@@ -335,6 +349,9 @@ def run_ours(a, rank, world, local_rank):
                      "traffic": TRAFFIC_BYTES_PER_LAUNCH if default_workload(a) else None, "peak_source": peak_src, "kernel": "search_kernel",
                      "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per_query * a.nq},
     }
+    if steady:
+        steady["frac_of_peak"] = steady["algorithmic_GBps"] / peak
+        line["config"]["steady_state"] = steady
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, h, qh_np[0])
     line["config"]["setup_s"] = time.perf_counter() - t_setup

@@ -360,7 +360,7 @@ def run_ours(a, rank, world, local_rank):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one search_kernel launch on the DEFAULT workload, from the
 # ncu --set full capture summarised in profiles/ (reported only when the run uses the default workload)
-TRAFFIC_BYTES_PER_LAUNCH = 6.476e9   # profiles/r1_final_search_kernel_ncu_full_selected.csv: 6.127 GB read + 0.349 GB written
+TRAFFIC_BYTES_PER_LAUNCH = 6.407e9   # profiles/r1_final_search_kernel_ncu_full_selected.csv: 6.078 GB read + 0.329 GB written
 
 
 def cpu_baseline(a, h, Q):

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
     // ---- layers level..0: ef_construction search + selection (hnsw.rs:1158-1205)
     for (int l = lv; l >= 0 && !overflow; --l) {
       if (!((mask >> l) & 1u)) continue;
-      search_layer<Op, CH, U, Queue>(g, s, stg, vis, Q, cur, p.ef_c, l, st, overflow, p.count - wi <= p.spec_tail);
+      search_layer<Op, CH, U, Queue>(g, s, stg, vis, Q, cur, p.ef_c, l, st, overflow);
       if (overflow) break;
       const int n = Q.n;
       const int nb = (l == 0) ? g.deg0 : g.M;  // 1177-1183

@@ -527,6 +527,39 @@ int hnsw_b200_export_vectors(const void* h, void* out) {
   HB_H(h);
   return pass(ix, ix->export_vectors(out));
 }
+// FlatNeighborhood::from(&hnsw) + get_neighbours(DataId) (flatten.rs:93-126): neighbours of `origin_id` over all
+// layers, ascending distance.  Returns the number written (<= cap), -1 when the id is unknown.
+int64_t hnsw_b200_flat_neighbours(const void* h, uint64_t origin_id, Neighbour_api* out, uint64_t cap) {
+  if (!h) return set_err("NULL handle");
+  Index* ix = ((const AnyApi*)h)->ix;
+  std::lock_guard<std::mutex> g(ix->mu);
+  std::vector<uint64_t> off, nbo;
+  std::vector<float> nbd;
+  if (pass(ix, ix->flatten(off, nbo, nbd))) return -1;
+  for (size_t p = 0; p < ix->n; ++p)
+    if (ix->h_origin[p] == origin_id) {
+      uint64_t c = 0;
+      for (uint64_t j = off[p]; j < off[p + 1] && c < cap; ++j, ++c) out[c] = Neighbour_api{(size_t)nbo[j], nbd[j]};
+      return (int64_t)c;
+    }
+  set_err("unknown origin id");
+  return -1;
+}
+// whole flattened graph: offsets[nb_point+1] (internal-id order), neighbour origin ids and distances; pass NULL
+// arrays to get the total neighbour count only
+int64_t hnsw_b200_flatten(const void* h, uint64_t* offsets, uint64_t* nb_origin, float* nb_dist) {
+  if (!h) return set_err("NULL handle");
+  Index* ix = ((const AnyApi*)h)->ix;
+  std::lock_guard<std::mutex> g(ix->mu);
+  std::vector<uint64_t> off, nbo;
+  std::vector<float> nbd;
+  if (pass(ix, ix->flatten(off, nbo, nbd))) return -1;
+  if (offsets) memcpy(offsets, off.data(), off.size() * 8);
+  if (nb_origin) memcpy(nb_origin, nbo.data(), nbo.size() * 8);
+  if (nb_dist) memcpy(nb_dist, nbd.data(), nbd.size() * 4);
+  return (int64_t)nbo.size();
+}
+
 int64_t hnsw_b200_layer_edges(const void* h, int layer) {
   if (!h) return set_err("NULL handle");
   Index* ix = ((const AnyApi*)h)->ix;

@@ -59,6 +59,34 @@ struct GraphView {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// L2 cache policies (createpolicy): vector rows stream through once per query (evict_first), the per-warp visited
+// tables are re-read for the whole search (evict_last), so that 6 GB of rows per launch do not push them out of L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_keep(const uint32_t* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_keep(uint32_t* p, uint32_t v, uint64_t pol) {
+  asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+
 // list of (p, layer): returns pointer to ids (or nullptr when the point owns no list there) and capacity
 __device__ __forceinline__ const uint32_t* list_ids(const GraphView& g, uint32_t p, int layer, int& cap) {
   if (layer == 0) {
@@ -374,6 +402,7 @@ __device__ __forceinline__ void warp_dists(const uint4* __restrict__ vec, int d4
                                            const uint32_t* ids, int n, float* out) {
   const int lane = lane_id();
   const int g = lane & 7, r = lane >> 3;
+  const uint64_t pol = l2_policy_evict_first();
   if constexpr (CH > 0) {
     uint4 qv[CH];
 #pragma unroll
@@ -390,7 +419,7 @@ __device__ __forceinline__ void warp_dists(const uint4* __restrict__ vec, int d4
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int i = 0; i < CH; ++i) x[u][i] = __ldg(row[u] + 8 * i);
+        for (int i = 0; i < CH; ++i) x[u][i] = ldg_stream(row[u] + 8 * i, pol);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         typename Op::acc_t a = Op::zero();
@@ -418,7 +447,7 @@ __device__ __forceinline__ void warp_dists(const uint4* __restrict__ vec, int d4
         uint4 qv = q4[g + 8 * i];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          uint4 x = __ldg(row[u] + 8 * i);
+          uint4 x = ldg_stream(row[u] + 8 * i, pol);
           Op::chunk(a[u], qv, x);
         }
       }
@@ -463,10 +492,12 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
   asm volatile(
@@ -505,7 +536,7 @@ __device__ __forceinline__ void warp_dists_staged(const uint4* __restrict__ vec,
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the stage precede the async writes
     if (lane == 0) mbar_expect_tx(st.bar, row_bytes * nst);
     __syncwarp();
-    if (lane < nst) bulk_g2s(st.buf + (size_t)lane * d4, vec + (size_t)ids[lane] * d4, row_bytes, st.bar);
+    if (lane < nst) bulk_g2s(st.buf + (size_t)lane * d4, vec + (size_t)ids[lane] * d4, row_bytes, st.bar, l2_policy_evict_first());
     if (n > STAGE_ROWS) warp_dists<Op, CH, U>(vec, d4, dim, q4, ids + STAGE_ROWS, n - STAGE_ROWS, out + STAGE_ROWS);
     const int g = lane & 7, r = lane >> 3;
     uint4 qv[CH];
@@ -584,11 +615,12 @@ struct Visited {
   // (match_any); the others probe on.  One L2 round trip per round, and almost always one round.
   __device__ __forceinline__ bool test_and_set(uint32_t id, bool valid) {
     const uint32_t want = tag | id;
+    const uint64_t pol_keep = l2_policy_evict_last();
     uint32_t h = (id * 2654435761u) >> shift;
     bool pending = valid, fresh = false;
     while (__any_sync(FULL, pending)) {
       uint32_t cur = 0;
-      if (pending) cur = __ldcg(tab + h);
+      if (pending) cur = ld_keep(tab + h, pol_keep);
       bool claim = false;
       if (pending) {
         if (cur == want) {
@@ -605,7 +637,7 @@ struct Visited {
         const int leader = __ffs(same) - 1;
         const uint32_t lead_id = __shfl_sync(claimers, id, leader);
         if (lane_id() == leader) {
-          __stcg(tab + h, want);
+          st_keep(tab + h, want, pol_keep);
           fresh = true;
           pending = false;
         } else if (lead_id == id) {
@@ -618,26 +650,6 @@ struct Visited {
     }
     used += __popc(__ballot_sync(FULL, fresh));  // warp-uniform count
     return fresh;
-  }
-  // Warp-collective read-only membership test (exact): true in the lanes whose id is in the set.
-  __device__ __forceinline__ bool contains(uint32_t id, bool valid) const {
-    const uint32_t want = tag | id;
-    uint32_t h = (id * 2654435761u) >> shift;
-    bool pending = valid, found = false;
-    while (__any_sync(FULL, pending)) {
-      if (pending) {
-        const uint32_t cur = __ldcg(tab + h);
-        if (cur == want) {
-          found = true;
-          pending = false;
-        } else if ((cur >> id_bits) != epoch) {
-          pending = false;  // free slot ends the probe chain: not present
-        } else {
-          h = (h + 1) & mask;
-        }
-      }
-    }
-    return found;
   }
   __device__ __forceinline__ bool overflowing() const { return used >= limit; }
 };
@@ -827,92 +839,9 @@ struct SmemQueueN {
   }
 };
 
-// Same queue held in registers: entry i lives in lane (i & 31), stripe (i >> 5); unused slots hold ~0 (whose
-// low bit reads as "expanded", so scans skip them).  Sorted insert = ballot rank + one shuffle-up per stripe.
-// No shared-memory traffic and no __syncwarp on the hot path.  Capacity 32*NS >= ef.
-template <int NS>
-struct RegQueue {
-  uint64_t w[NS];
-  int n;
-  int cap;
-  uint64_t fkey;  // largest key (flag cleared) when full, else ~0; warp-uniform
-
-  __device__ __forceinline__ void reset(uint64_t*, int ef) {
-#pragma unroll
-    for (int s = 0; s < NS; ++s) w[s] = ~0ull;
-    n = 0;
-    cap = ef;
-    fkey = ~0ull;
-  }
-  __device__ __forceinline__ void clear() { reset(nullptr, cap); }
-  __device__ __forceinline__ uint64_t get(int i) const {
-    uint64_t v = 0;
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-      if ((i >> 5) == s) v = w[s];
-    return __shfl_sync(FULL, v, i & 31);
-  }
-  __device__ __forceinline__ uint64_t local(int i) const {  // entry i for the lane with lane == (i & 31)
-    uint64_t v = ~0ull;
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-      if ((i >> 5) == s) v = w[s];
-    return v;
-  }
-  __device__ __forceinline__ void mark_expanded(int i) {
-    const bool mine = lane_id() == (i & 31);
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-      if (mine && (i >> 5) == s) w[s] |= 1ull;
-  }
-  __device__ __forceinline__ void push_first(uint64_t key) {
-    reset(nullptr, cap);
-    if (lane_id() == 0) w[0] = key;
-    n = 1;
-    fkey = cap == 1 ? key : ~0ull;
-  }
-  __device__ __forceinline__ int first_unexpanded() const { return next_unexpanded(0); }
-  __device__ __forceinline__ int next_unexpanded(int from) const {
-    const int lane = lane_id();
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const unsigned m = __ballot_sync(FULL, ((w[s] & 1ull) == 0ull) && (32 * s + lane >= from));
-      if (m) return 32 * s + __ffs(m) - 1;
-    }
-    return -1;
-  }
-  __device__ __forceinline__ void next3(int from, int& a, int& b, int& c) const {
-    a = next_unexpanded(from);
-    b = a >= 0 ? next_unexpanded(a + 1) : -1;
-    c = b >= 0 ? next_unexpanded(b + 1) : -1;
-  }
-  __device__ __forceinline__ bool accepts(uint64_t key) const { return n < cap || key < fkey; }
-  __device__ __forceinline__ void insert(uint64_t key) {
-    const int lane = lane_id();
-    int pos = 0;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) pos += __popc(__ballot_sync(FULL, w[s] < key));
-#pragma unroll
-    for (int s = NS - 1; s >= 0; --s) {
-      const uint64_t up = __shfl_up_sync(FULL, w[s], 1);
-      uint64_t carry = 0;
-      if (s > 0) carry = __shfl_sync(FULL, w[s - 1], 31);
-      const int i = 32 * s + lane;
-      const uint64_t moved = lane == 0 ? carry : up;
-      uint64_t nv = i > pos ? moved : (i == pos ? key : w[s]);
-      if (i >= cap) nv = ~0ull;
-      w[s] = nv;
-    }
-    n = n < cap ? n + 1 : cap;
-    fkey = n == cap ? (get(cap - 1) & ~1ull) : ~0ull;
-  }
-};
-
-// queue kinds: 0 = generic SortedQueue (any ef), 100 + NCH = SmemQueueN<NCH> (ef <= 32*NCH), other = RegQueue<NS>
+// queue kinds: 0 = generic SortedQueue (any ef), 100 + NCH = SmemQueueN<NCH> (ef <= 32*NCH)
 template <int KIND>
-struct QueueSel {
-  typedef RegQueue<KIND> type;
-};
+struct QueueSel;
 template <> struct QueueSel<0> { typedef SortedQueue type; };
 template <> struct QueueSel<101> { typedef SmemQueueN<1> type; };
 template <> struct QueueSel<102> { typedef SmemQueueN<2> type; };

@@ -16,14 +16,6 @@ namespace hb {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
-// Last-wave speculation threshold = slots * pct / 100.  Measured on B200 (profiles/README.md): speculation is exact
-// but never faster (2.04 ms -> 2.15-2.20 ms per 10k queries for pct = 50..150), so it is OFF unless
-// HNSW_B200_SPEC_TAIL=<pct> asks for it.
-static uint32_t spec_tail_items(size_t slots) {
-  static const int pct = [] { const char* e = getenv("HNSW_B200_SPEC_TAIL"); return e ? atoi(e) : 0; }();
-  return (uint32_t)(slots * (size_t)pct / 100);
-}
-
 static size_t next_pow2(size_t x) {
   size_t p = 1;
   while (p < x) p <<= 1;
@@ -280,7 +272,6 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
     int r;
     if ((r = ensure_visited((size_t)grid * wpb, vcap))) return r;
     if ((r = fill_visited_cfg(p.vis))) return r;
-    p.spec_tail = spec_tail_items((size_t)grid * wpb);
     HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
     HB_CUDA(launch_insert_search(p, metric, dtype, grid, smem, stream_, false, nullptr));
     int status = 0;
@@ -576,7 +567,6 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
       p.cbuf = (uint64_t*)d_cbuf_;
       p.ccap = (uint32_t)vis_cap_;
     }
-    p.spec_tail = spec_tail_items((size_t)grid * wpb);
     HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
     HB_CUDA(cudaEventRecord(ev0_, stream_));
     if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, grid, smem, stream_, false, nullptr));
@@ -737,6 +727,36 @@ int Index::export_layer(int layer, uint64_t* offsets, uint32_t* ids, float* dist
   }
   if (offsets) offsets[n] = o;
   if (total) *total = (int64_t)o;
+  return 0;
+}
+
+int Index::flatten(std::vector<uint64_t>& offsets, std::vector<uint64_t>& nb_origin, std::vector<float>& nb_dist) const {
+  std::vector<std::vector<std::pair<float, uint32_t>>> per(n);
+  int top = 0;
+  for (size_t p = 0; p < n; ++p) top = std::max<int>(top, h_plevel[p]);
+  for (int l = 0; l <= top && l < MAX_LAYERS; ++l) {
+    int64_t total = 0;
+    int r;
+    if ((r = export_layer(l, nullptr, nullptr, nullptr, &total))) return r;
+    std::vector<uint64_t> off(n + 1);
+    std::vector<uint32_t> ids((size_t)total);
+    std::vector<float> ds((size_t)total);
+    if ((r = export_layer(l, off.data(), ids.data(), ds.data(), nullptr))) return r;
+    for (size_t p = 0; p < n; ++p)
+      for (uint64_t j = off[p]; j < off[p + 1]; ++j) per[p].emplace_back(ds[j], ids[j]);
+  }
+  offsets.assign(n + 1, 0);
+  nb_origin.clear();
+  nb_dist.clear();
+  for (size_t p = 0; p < n; ++p) {
+    std::sort(per[p].begin(), per[p].end());  // flatten.rs:82 sort_unstable by distance (ties: by internal id here)
+    offsets[p] = nb_origin.size();
+    for (auto& e : per[p]) {
+      nb_origin.push_back(h_origin[e.second]);
+      nb_dist.push_back(e.first);
+    }
+  }
+  offsets[n] = nb_origin.size();
   return 0;
 }
 

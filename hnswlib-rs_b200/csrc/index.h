@@ -94,6 +94,9 @@ class Index {
 
   int export_layer(int layer, uint64_t* offsets, uint32_t* ids, float* dists, int64_t* total) const;
   int export_vectors(void* out) const;
+  // FlatNeighborhood (/root/reference/src/flatten.rs:50-126): per point, the neighbours of ALL layers merged and
+  // sorted by distance; CSR over internal ids, neighbours named by origin id
+  int flatten(std::vector<uint64_t>& offsets, std::vector<uint64_t>& nb_origin, std::vector<float>& nb_dist) const;
   // dump / reload in the reference's two-file format (hnswio.cu)
   int file_dump(const std::string& dir, const std::string& basename, bool overwrite, std::string* used_basename);
   int load_dump(const std::string& dir, const std::string& basename);

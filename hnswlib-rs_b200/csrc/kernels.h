@@ -41,7 +41,6 @@ struct SearchParams {
   int smem_per_warp;
   int q_smem;  // queue slots in shared memory
   int q_kind;  // QueueSel kind
-  uint32_t spec_tail;  // work items with fewer than this many items left after them speculate (last wave)
   uint64_t* cbuf;  // filtered search only: candidate queue C, [slots][ccap] keys
   uint32_t ccap;
 };
@@ -50,8 +49,8 @@ struct SearchParams {
 __host__ __device__ inline size_t stage_bytes(int d4) { return d4 <= 32 ? (size_t)STAGE_ROWS * d4 * 16 : 0; }
 // register-queue stripes for a given ef (0 = queue in shared memory)
 // Queue kind for a given ef (see QueueSel): compile-time chunked shared-memory queue up to ef = 256, generic beyond.
-// (A register-resident variant, RegQueue, exists in common.cuh; measured ~5 % slower at 64 registers/thread because
-// it spills, so it is not instantiated.)
+// (A register-resident variant was measured ~5 % slower at 64 registers/thread because it spills, and a speculative
+// two-candidates-per-iteration loop was exact but 5-13 % slower; both were removed, see profiles/README.md.)
 inline int queue_kind(int ef, int metric, int dtype) {
   const bool common = dtype == DT_F32 && (metric == METRIC_L1 || metric == METRIC_L2 || metric == METRIC_DOT || metric == METRIC_COSINE);
   if (!common || ef > 256) return 0;
@@ -82,7 +81,6 @@ struct InsertParams {
   int smem_per_warp;
   int q_smem;
   int q_kind;
-  uint32_t spec_tail;
 };
 
 inline size_t insert_smem_per_warp(int d4, int ef_c, int deg0, int q_smem) {

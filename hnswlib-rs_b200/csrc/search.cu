@@ -89,8 +89,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
         pivot = new_pivot;  // hnsw.rs:1526-1528
       }
       // ---- layer-0 (lowest populated layer) search, hnsw.rs:1531-1542
-      search_layer<Op, CH, U, Queue>(g, s, stg, vis, Q, pivot, p.ef, p.layer0, st, overflow,
-                                     /*speculate=*/p.nq - qi <= p.spec_tail);
+      search_layer<Op, CH, U, Queue>(g, s, stg, vis, Q, pivot, p.ef, p.layer0, st, overflow);
       count = min(p.k, min(p.ef, Q.n));  // hnsw.rs:1547
     }
     if (overflow) {

@@ -9,7 +9,7 @@ namespace hb {
 struct WarpSmem {
   uint4* q4;          // query row, d4 16-byte chunks (zero padded)
   uint64_t* wbuf;     // queue keys, capacity >= ef
-  uint32_t* cand_id;  // 64 (a chunk of the current candidate + a speculative chunk of the next one)
+  uint32_t* cand_id;  // 64 slots reserved, 32 used (one chunk of neighbours)
   float* cand_d;      // 64
 };
 
@@ -26,8 +26,7 @@ struct Stats {
 // Ties on distance are ordered by id (oracle MODE_DET).
 template <class Op, int CH, int U, class Queue>
 __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem& s, Stage& stg, Visited& vis,
-                                             Queue& Q, uint32_t ep, int ef, int layer, Stats& st, bool& overflow,
-                                             bool speculate = false) {
+                                             Queue& Q, uint32_t ep, int ef, int layer, Stats& st, bool& overflow) {
   const int lane = lane_id();
   const uint4* vec4 = reinterpret_cast<const uint4*>(g.vec);
   vis.begin();
@@ -47,59 +46,34 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
     const uint32_t c = key_id(Q.get(idx));
     int cap;
     const uint32_t* ids = list_ids(g, c, layer, cap);  // hnsw.rs:1006
-    // ---- speculation (only for work items of the LAST wave, when the machine is draining and latency, not issue
-    // bandwidth, bounds the launch): the nearest OTHER unexpanded entry is the next pick ~88 % of the time (oracle
-    // study).  Its neighbour rows are fetched together with c's; its results are committed only if it really is the
-    // next pick once c's neighbours are in the queue, otherwise they are dropped and no state has changed.
-    // At full load the extra probe and the 12 % wasted rows cost more than the shorter chain gains (measured).
-    // the next unexpanded entries after idx, found in one pass: speculation target (when enabled) and L2 prefetch
-    int n1, n2, n3;
-    Q.next3(idx + 1, n1, n2, n3);
-    int i2 = -1;
-    uint32_t c2 = INVALID_ID;
-    const uint32_t* ids2 = nullptr;
-    if (speculate && cap <= 32 && ef > 1 && n1 >= 0) {
-      i2 = n1;
-      c2 = key_id(Q.get(i2));
-      int cap2;
-      ids2 = list_ids(g, c2, layer, cap2);
-      if (!ids2) c2 = INVALID_ID;
-    }
-    Q.mark_expanded(idx);
-    st.expansions += 1;
-    {  // pull the adjacency rows of the following candidates towards L2
-      const int i3 = i2 >= 0 ? n2 : n1;
-      const int i4 = i2 >= 0 ? n3 : n2;
-      const uint32_t c3 = i3 >= 0 ? key_id(Q.get(i3)) : INVALID_ID;
-      const uint32_t c4 = i4 >= 0 ? key_id(Q.get(i4)) : INVALID_ID;
-      const uint32_t pc = lane == 0 ? c3 : (lane == 1 ? c4 : INVALID_ID);
+    {  // pull the adjacency rows of the two most likely next candidates towards L2 while this one is expanded
+      int n1, n2, n3;
+      Q.next3(idx + 1, n1, n2, n3);
+      const uint32_t c1 = n1 >= 0 ? key_id(Q.get(n1)) : INVALID_ID;
+      const uint32_t c2 = n2 >= 0 ? key_id(Q.get(n2)) : INVALID_ID;
+      const uint32_t pc = lane == 0 ? c1 : (lane == 1 ? c2 : INVALID_ID);
       if (pc != INVALID_ID) {
         int pcap;
         const uint32_t* pids = list_ids(g, pc, layer, pcap);
         if (pids) asm volatile("prefetch.global.L2 [%0];" ::"l"(pids));
       }
     }
-    if (cap <= 32) {
-      const uint32_t nid = lane < cap ? ids[lane] : INVALID_ID;
-      const uint32_t nid2 = (c2 != INVALID_ID && lane < cap) ? ids2[lane] : INVALID_ID;
-      st.adj += __popc(__ballot_sync(FULL, nid != INVALID_ID));
+    Q.mark_expanded(idx);
+    st.expansions += 1;
+    for (int base = 0; base < cap; base += 32) {  // hnsw.rs:1013, 32 neighbours at a time
+      const uint32_t nid = (base + lane < cap) ? ids[base + lane] : INVALID_ID;
+      const unsigned valid = __ballot_sync(FULL, nid != INVALID_ID);
+      st.adj += __popc(valid);
       const bool fresh = vis.test_and_set(nid, nid != INVALID_ID);  // hnsw.rs:1016-1017
-      // c2's neighbours not yet visited (c's fresh ones are already in the table): read-only, nothing is recorded
-      bool seen2 = true;  // contains() is warp-collective: call it under a warp-uniform condition only
-      if (c2 != INVALID_ID) seen2 = vis.contains(nid2, nid2 != INVALID_ID);
-      const bool spec = (nid2 != INVALID_ID) && !seen2;
-      const unsigned m1 = __ballot_sync(FULL, fresh), m2 = __ballot_sync(FULL, spec);
-      const int cnt = __popc(m1), cnt2 = __popc(m2);
-      const unsigned lt = (1u << lane) - 1u;
-      if (cnt + cnt2) {
-        if (fresh) s.cand_id[__popc(m1 & lt)] = nid;
-        if (spec) s.cand_id[cnt + __popc(m2 & lt)] = nid2;
+      const unsigned m = __ballot_sync(FULL, fresh);
+      const int cnt = __popc(m);
+      if (cnt) {
+        const int pos = __popc(m & ((1u << lane) - 1u));
+        if (fresh) s.cand_id[pos] = nid;
         __syncwarp();
-        warp_dists_staged<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, cnt + cnt2, s.cand_d, stg);  // hnsw.rs:1026
+        warp_dists_staged<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, cnt, s.cand_d, stg);  // hnsw.rs:1026
         __syncwarp();
-      }
-      st.evals += cnt;
-      {
+        st.evals += cnt;
         const uint64_t key = lane < cnt ? make_key(Op::post(s.cand_d[lane]), s.cand_id[lane]) : ~0ull;
         unsigned acc = __ballot_sync(FULL, lane < cnt && Q.accepts(key));  // hnsw.rs:1028
         while (acc) {
@@ -109,50 +83,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, const WarpSmem&
           if (Q.accepts(kj)) Q.insert(kj);  // hnsw.rs:1035-1053
         }
       }
-      if (c2 != INVALID_ID) {
-        const int j2 = Q.first_unexpanded();
-        if (j2 >= 0 && key_id(Q.get(j2)) == c2) {  // speculation holds: this IS the next C.pop()
-          Q.mark_expanded(j2);
-          st.expansions += 1;
-          st.adj += __popc(__ballot_sync(FULL, nid2 != INVALID_ID));
-          vis.test_and_set(nid2, spec);  // now record them (all fresh by construction)
-          st.evals += cnt2;
-          const uint64_t key = lane < cnt2 ? make_key(Op::post(s.cand_d[cnt + lane]), s.cand_id[cnt + lane]) : ~0ull;
-          unsigned acc = __ballot_sync(FULL, lane < cnt2 && Q.accepts(key));
-          while (acc) {
-            const int j = __ffs(acc) - 1;
-            acc &= acc - 1;
-            const uint64_t kj = __shfl_sync(FULL, key, j);
-            if (Q.accepts(kj)) Q.insert(kj);
-          }
-        }
-      }
-    } else {
-      for (int base = 0; base < cap; base += 32) {  // hnsw.rs:1013, 32 neighbours at a time
-        const uint32_t nid = (base + lane < cap) ? ids[base + lane] : INVALID_ID;
-        const unsigned valid = __ballot_sync(FULL, nid != INVALID_ID);
-        st.adj += __popc(valid);
-        const bool fresh = vis.test_and_set(nid, nid != INVALID_ID);  // hnsw.rs:1016-1017
-        const unsigned m = __ballot_sync(FULL, fresh);
-        const int cnt = __popc(m);
-        if (cnt) {
-          const int pos = __popc(m & ((1u << lane) - 1u));
-          if (fresh) s.cand_id[pos] = nid;
-          __syncwarp();
-          warp_dists_staged<Op, CH, U>(vec4, g.d4, g.dim, s.q4, s.cand_id, cnt, s.cand_d, stg);  // hnsw.rs:1026
-          __syncwarp();
-          st.evals += cnt;
-          const uint64_t key = lane < cnt ? make_key(Op::post(s.cand_d[lane]), s.cand_id[lane]) : ~0ull;
-          unsigned acc = __ballot_sync(FULL, lane < cnt && Q.accepts(key));  // hnsw.rs:1028
-          while (acc) {
-            const int j = __ffs(acc) - 1;
-            acc &= acc - 1;
-            const uint64_t kj = __shfl_sync(FULL, key, j);
-            if (Q.accepts(kj)) Q.insert(kj);  // hnsw.rs:1035-1053
-          }
-        }
-        if (valid != FULL) break;  // lists are dense prefixes terminated by INVALID_ID
-      }
+      if (valid != FULL) break;  // lists are dense prefixes terminated by INVALID_ID
     }
     if (vis.overflowing()) {
       overflow = true;

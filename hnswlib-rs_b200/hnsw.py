@@ -93,6 +93,10 @@ def load_library():
     L.hnsw_b200_layer_edges.restype = i64
     L.hnsw_b200_layer_edges.argtypes = [vp, i32]
     L.hnsw_b200_export_layer.argtypes = [vp, i32, vp, vp, vp]
+    L.hnsw_b200_flat_neighbours.restype = i64
+    L.hnsw_b200_flat_neighbours.argtypes = [vp, u64, vp, u64]
+    L.hnsw_b200_flatten.restype = i64
+    L.hnsw_b200_flatten.argtypes = [vp, vp, vp, vp]
     L.hnsw_b200_import_graph.argtypes = [vp, vp, u64, u64, vp, vp, i64, i32, vp, vp, vp]
     L.hnsw_b200_blob_header.argtypes = [vp, vp]
     L.hnsw_b200_blob_alloc.argtypes = [vp, vp]
@@ -414,6 +418,18 @@ class Hnsw:
         off, ids, ds = np.empty(n + 1, np.uint64), np.empty(ne, np.uint32), np.empty(ne, np.float32)
         self._chk(self._L.hnsw_b200_export_layer(self._h, layer, _p(off), _p(ids), _p(ds)))
         return off, ids, ds
+
+    def flat_neighborhood(self):
+        """FlatNeighborhood::from(&hnsw) (flatten.rs:93-126): dict DataId -> [(neighbour DataId, distance)] ascending."""
+        n = self.get_nb_point()
+        tot = int(self._L.hnsw_b200_flatten(self._h, None, None, None))
+        if tot < 0:
+            raise HnswError(last_error())
+        off, ids, ds = np.empty(n + 1, np.uint64), np.empty(tot, np.uint64), np.empty(tot, np.float32)
+        self._L.hnsw_b200_flatten(self._h, _p(off), _p(ids), _p(ds))
+        og = self.export_points()[2]
+        return {int(og[p]): list(zip(ids[int(off[p]):int(off[p + 1])].tolist(), ds[int(off[p]):int(off[p + 1])].tolist()))
+                for p in range(n)}
 
     def import_graph(self, vecs, origin, levels, entry, layers):
         """layers: list (index = layer) of (offsets u64[N+1], ids u32[], dists f32[]|None)."""

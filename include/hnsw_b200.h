@@ -269,6 +269,11 @@ int hnsw_b200_export_points(const void* h, uint8_t* levels, int32_t* ranks, uint
 int hnsw_b200_export_vectors(const void* h, void* out /* [nb_point][dim] elements */);
 int64_t hnsw_b200_layer_edges(const void* h, int layer);
 int hnsw_b200_export_layer(const void* h, int layer, uint64_t* offsets, uint32_t* ids, float* dists);
+/* FlatNeighborhood (/root/reference/src/flatten.rs:50-126): the graph-only view, neighbours of all layers merged and
+ * sorted by distance.  flat_neighbours = get_neighbours(DataId); flatten = the whole table (call with NULL arrays first
+ * to size them: returns the total neighbour count). */
+int64_t hnsw_b200_flat_neighbours(const void* h, uint64_t origin_id, Neighbour_api* out, uint64_t cap);
+int64_t hnsw_b200_flatten(const void* h, uint64_t* offsets, uint64_t* nb_origin, float* nb_dist);
 /* import into an EMPTY handle: nlayers CSR layers (layer l at offsets[l], ids[l], dists[l]; dists[l] may be NULL) */
 int hnsw_b200_import_graph(void* h, const void* vecs, uint64_t n, uint64_t dim, const uint64_t* origin,
                            const uint8_t* levels, int64_t entry, int nlayers, const uint64_t* const* offsets,

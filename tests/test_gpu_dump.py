@@ -84,3 +84,37 @@ def test_empty_index_dump_is_an_error(tmp_path, pkg):
     h = pkg.Hnsw(8, 10, 16, 20, "DistL2")
     with pytest.raises(pkg.HnswError):
         h.file_dump(tmp_path, "empty")
+
+
+def test_flat_neighborhood_matches_oracle_lists(pkg, po):
+    """FlatNeighborhood (flatten.rs:50-126): all layers merged, ascending distance; flatten.rs:146-197 checks it is
+    identical before and after a dump/reload."""
+    import tempfile
+    n, d = 1500, 10
+    X = pkg.datagen.uniform(n, d, 12)
+    o = po.Oracle(6, n, 16, 40, "DistL2", d, mode=po.MODE_DET, order=po.ORDER_GPU)
+    lv = o.draw_levels(n)
+    o.insert_batch(X, ids=np.arange(300, 300 + n), levels=lv)
+    h = pkg.Hnsw(6, n, 16, 40, "DistL2")
+    h.set_insert_batching(1 << 30, 1)
+    h.insert_flat(X, ids=np.arange(300, 300 + n), levels=lv)
+    flat = h.flat_neighborhood()
+    olv, ork, oog = o.export_points()
+    layers = [o.export_layer(l) for l in range(int(olv.max()) + 1)]
+    for p in (0, 5, 77, n - 1):
+        own, full = [], []   # oracle lists of layers <= the point's level / of all 16 layers
+        for l, (off, ids, ds) in enumerate(layers):
+            item = [(np.float32(ds[j]), int(oog[ids[j]])) for j in range(int(off[p]), int(off[p + 1]))]
+            full += item
+            if l == 0 or olv[p] >= l:
+                own += item
+        got = [(np.float32(dd), i) for i, dd in flat[int(oog[p])]]
+        assert got == sorted(got, key=lambda t: t[0])            # ascending distance (flatten.rs:82)
+        # the engine materialises every list a search can reach: at least the layers up to the point's level, plus
+        # (for former entry points) the layers it was promoted to; never a list the oracle does not have
+        assert set(own) <= set(got) <= set(full)
+    with tempfile.TemporaryDirectory() as td:
+        h.file_dump(td, "fl")
+        h2 = pkg.Hnsw.load(td, "fl", "DistL2")
+        flat2 = h2.flat_neighborhood()
+    assert all(flat[k] == flat2[k] for k in flat)

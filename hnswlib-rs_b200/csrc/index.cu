@@ -253,7 +253,7 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
   p.extend = extend_candidates ? 1 : 0;
   p.work_counter = d_counter_;
   p.locks = d_locks_.p;
-  p.stats = nullptr;
+  p.stats = stats_on_ ? d_stats_ : nullptr;  // insert-path distance evaluations / expansions / adjacency ids read
   p.status = d_status_;
   p.q_kind = queue_kind(ef_c, metric, dtype);
   if (p.q_kind != 0 && p.q_kind < 104) p.q_kind = 104;  // the insert kernel is built for 128 / 256-slot queues only

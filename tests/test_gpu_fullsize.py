@@ -1,0 +1,62 @@
+"""Full-size checks at BASELINE.json configs[1] (1 000 000 x 128 f32 L2, M=16, ef_c=200, 10 000 queries, ef=64): the oracle
+cannot run this size in seconds, so the engine is checked through size-independent properties (sortedness, idempotence,
+self-retrieval, permutation invariance, agreement with the exact brute-force kernel) plus an oracle spot-check of a
+query sample on the SAME graph (exported from the GPU, imported into the oracle)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2(pkg):
+    n, d = 1000000, 128
+    X = pkg.datagen.clustered(n, d, 1)
+    h = pkg.Hnsw(16, n, 16, 200, "DistL2")
+    h.insert_flat(X)
+    Q = pkg.datagen.clustered(10000, d, 2)
+    return X, Q, h
+
+
+def test_fullsize_properties(pkg, c2):
+    X, Q, h = c2
+    assert h.get_nb_point() == len(X)
+    o, d, it, pid, cnt = h.search_flat(Q, 10, 64)
+    assert np.all(cnt == 10)
+    assert np.all(np.diff(d, axis=1) >= 0)                                  # ascending (hnsw.rs:1544)
+    assert np.all(it < len(X)) and np.all(o == it)                          # default origin id == insertion rank
+    assert all(len(set(row.tolist())) == 10 for row in it[:2000])           # no duplicate neighbour
+    o2, d2, it2, _, cnt2 = h.search_flat(Q, 10, 64)                         # idempotent
+    assert np.array_equal(it, it2) and np.array_equal(d.view(np.uint32), d2.view(np.uint32))
+    perm = np.random.default_rng(0).permutation(len(Q))                     # answers follow the input order
+    o3, d3, it3, _, _ = h.search_flat(Q[perm], 10, 64)
+    assert np.array_equal(it3, it[perm]) and np.array_equal(d3, d[perm])
+    # returned distances are the true distances to the returned points (f64 check, 1e-5 relative)
+    for i in (0, 17, 9999):
+        ref = np.sqrt(((X[it[i]].astype(np.float64) - Q[i].astype(np.float64)) ** 2).sum(1))
+        assert np.allclose(d[i], ref, rtol=1e-5)
+    # k / ef monotonicity: the top-5 of (k=5) equals the first 5 of (k=10) at the same ef
+    o5, d5, it5, _, _ = h.search_flat(Q[:500], 5, 64)
+    assert np.array_equal(it5, it[:500, :5])
+    # self retrieval: stored points find themselves at distance 0 (tests/equality.rs logs this rate)
+    s = h.search_flat(X[:2000], 1, 64)
+    assert (s[2][:, 0] == np.arange(2000)).mean() > 0.97 and np.all(s[1][s[2][:, 0] == np.arange(2000), 0] == 0.0)
+
+
+def test_fullsize_recall_and_oracle_spotcheck(pkg, po, c2):
+    X, Q, h = c2
+    o, d, it, pid, cnt = h.search_flat(Q[:1000], 10, 64)
+    bi, bd = h.bruteforce(Q[:1000], 10)                                     # exact, K5 kernel
+    rec = np.mean([len(set(it[i].tolist()) & set(bi[i].tolist())) / 10 for i in range(1000)])
+    ball = np.mean([(d[i] <= bd[i, 9]).sum() / 10 for i in range(1000)])    # the reference's recall definition
+    assert rec > 0.8 and ball >= rec
+    # brute force itself against numpy on a few queries
+    for i in (0, 500):
+        dd = np.sqrt(((X.astype(np.float32) - Q[i]) ** 2).sum(1))
+        assert set(np.argsort(dd, kind="stable")[:10].tolist()) == set(bi[i].tolist())
+    # oracle on the same graph (MODE_DET + GPU summation order): identical answers for a query sample
+    lv, rk, og, entry = h.export_points()
+    orc = po.Oracle(16, len(X), 16, 200, "DistL2", 128, mode=po.MODE_DET, order=po.ORDER_GPU)
+    orc.import_graph(X, og, lv, entry, {l: h.export_layer(l) for l in range(int(lv.max()) + 1)})
+    oo, od, oi, _, oc = orc.search_batch(Q[:300], 10, 64, nthreads=8)
+    assert np.array_equal(oi, it[:300]) and np.array_equal(od.view(np.uint32), d[:300].view(np.uint32))

@@ -547,7 +547,6 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
     }
   }
   if (bps < 1) return fail("search kernel does not fit on an SM");
-  if (const char* e = getenv("HNSW_B200_SEARCH_CTAS")) bps = std::max(1, std::min(bps, atoi(e)));  // tuning knob
   int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (nq + wpb - 1) / wpb);
   const int deg = layer0 == 0 ? 2 * M : M;
   size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)2 * (p.ef + 16) * deg));

@@ -189,7 +189,7 @@ def run_reference(a, rank, world):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -355,7 +355,7 @@ def run_ours(a, rank, world, local_rank):
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, h, qh_np[0])
     line["config"]["setup_s"] = time.perf_counter() - t_setup
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one search_kernel launch on the DEFAULT workload, from the
@@ -386,11 +386,46 @@ def cpu_baseline(a, h, Q):
             "sample": f"{reps} passes over the same {a.nq}-query batch on the GPU-built graph ({dt:.1f} s wall)"}
 
 
+class _OnlyJsonOnStdout:
+    """Everything a library prints to stdout while the benchmark runs (NCCL's version banner, ...) goes to stderr, so
+    that rank 0's stdout carries exactly one line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def emit(line):
+    """called inside _OnlyJsonOnStdout: write the JSON line to the REAL stdout"""
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT[0], (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = [1]
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    guard = _OnlyJsonOnStdout()
+    guard.__enter__()
+    _REAL_STDOUT[0] = guard.saved
+    try:
+        _main_guarded(a, rank, world, local_rank)
+    finally:
+        guard.__exit__()
+
+
+def _main_guarded(a, rank, world, local_rank):
     if a.impl == "reference":
         run_reference(a, rank, world)
         return

@@ -32,6 +32,9 @@
 //
 // Internal id of a point = its insertion rank (0-based).  PointId(level, rank-in-level) of the
 // reference is kept per point for the Neighbour output.
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -608,7 +611,30 @@ static void do_search_batch(Index<T>* ix, const void* qs, size_t nq, size_t k, s
     }
 }
 
+// Memory placement for the CPU baseline: interleave the calling thread's future allocations over all NUMA nodes
+// (set_mempolicy(MPOL_INTERLEAVE)), as a multi-threaded build would spread them by first touch; on = 0 restores the
+// default policy.  Returns 0 on success, -1 when the kernel refuses (single node, container policy): harmless.
+static int set_interleave(int on) {
+#ifdef SYS_set_mempolicy
+  unsigned long mask[16];
+  for (int i = 0; i < 16; ++i) mask[i] = ~0ul;
+  long r = on ? syscall(SYS_set_mempolicy, 3 /*MPOL_INTERLEAVE*/, mask, 1024ul) : syscall(SYS_set_mempolicy, 0, nullptr, 0ul);
+  if (r != 0 && on) {  // retry with a small node mask (kernels reject bits beyond the possible nodes on some configs)
+    for (int nodes = 8; nodes >= 2 && r != 0; nodes /= 2) {
+      unsigned long m1 = (1ul << nodes) - 1;
+      r = syscall(SYS_set_mempolicy, 3, &m1, (unsigned long)nodes + 1);
+    }
+  }
+  return r == 0 ? 0 : -1;
+#else
+  (void)on;
+  return -1;
+#endif
+}
+
 extern "C" {
+
+int oracle_numa_interleave(int on) { return set_interleave(on); }
 
 void* oracle_new(int dtype, int M, uint64_t max_elements, int max_layer, int ef_c, int metric, int dim) {
   OracleHandle* h = new OracleHandle{dtype, nullptr};

@@ -62,6 +62,8 @@ def lib():
         L.oracle_dist.restype = C.c_float
         L.oracle_dist.argtypes = [i32, i32, i32, vp, vp, u64]
         L.oracle_bruteforce.argtypes = [i32, i32, i32, vp, u64, vp, u64, u64, u64, i32, vp, vp]
+        L.oracle_numa_interleave.restype = i32
+        L.oracle_numa_interleave.argtypes = [i32]
         L.oracle_rheap_script.restype = u64
         L.oracle_rheap_script.argtypes = [vp, vp, u64, i32, i32, vp]
         _LIB = L
@@ -70,6 +72,11 @@ def lib():
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def numa_interleave(on=True):
+    """interleave this thread's future allocations over all NUMA nodes (CPU-baseline fairness); 0 ok, -1 refused"""
+    return int(lib().oracle_numa_interleave(int(bool(on))))
 
 
 def dist(a, b, metric, order=ORDER_REF):

@@ -1,0 +1,49 @@
+/* Minimal C caller of libhnsw_b200.so through the reference's own entry points (libext.rs names):
+ * build an index, search it, release everything.  Also proves include/hnsw_b200.h is plain C.
+ *   gcc -std=c99 -Iinclude examples/c_demo.c -Lhnswlib-rs_b200/lib -lhnsw_b200 -Wl,-rpath,$PWD/hnswlib-rs_b200/lib -o c_demo
+ * Without a usable CUDA device the constructor returns NULL and the demo prints the library's error (no CPU fallback). */
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "hnsw_b200.h"
+
+int main(void) {
+  const char* name = "DistL2";
+  const HnswApif32* h = init_hnsw_f32(16, 200, 6, (const uint8_t*)name);
+  if (!h) {
+    printf("init_hnsw_f32 failed: %s\n", hnsw_b200_last_error());
+    return 2;
+  }
+  enum { N = 2000, D = 16 };
+  float* data = (float*)malloc(sizeof(float) * N * D);
+  const float** rows = (const float**)malloc(sizeof(float*) * N);
+  size_t* ids = (size_t*)malloc(sizeof(size_t) * N);
+  unsigned s = 12345u;
+  for (int i = 0; i < N * D; ++i) {
+    s = s * 1664525u + 1013904223u;
+    data[i] = (float)(s >> 8) / 16777216.0f;
+  }
+  for (int i = 0; i < N; ++i) {
+    rows[i] = data + (size_t)i * D;
+    ids[i] = 1000 + (size_t)i;
+  }
+  parallel_insert_f32((HnswApif32*)h, N, D, rows, ids);
+  const Neighbourhood_api* r = search_neighbours_f32(h, D, rows[7], 5, 32);
+  if (!r) {
+    printf("search failed: %s\n", hnsw_b200_last_error());
+    return 3;
+  }
+  printf("query = stored point 7: %lld neighbours, nearest id %zu at distance %g\n", (long long)r->nbgh,
+         r->neighbours[0].id, (double)r->neighbours[0].d);
+  int ok = r->nbgh == 5 && r->neighbours[0].id == 1007 && r->neighbours[0].d == 0.0f;
+  hnsw_b200_free_neighbourhood(r);
+  const Vec_api_Neighbourhood_api* v = parallel_search_neighbours_f32(h, 3, D, rows, 4, 32);
+  ok = ok && v && v->len == 3 && v->ptr[2].neighbours[0].id == 1002;
+  hnsw_b200_free_vec_api(v);
+  drop_hnsw_f32(h);
+  free(data);
+  free(rows);
+  free(ids);
+  printf(ok ? "c_demo ok\n" : "c_demo FAILED\n");
+  return ok ? 0 : 1;
+}

@@ -114,3 +114,42 @@ def test_error_paths_are_loud(pkg):
         pkg.Hnsw(1, 10, 16, 20, "DistL2")      # ln(1) = 0 breaks the level law
     with pytest.raises(pkg.HnswError):
         h.modify_level_scale(0.5)               # only before the first insert (hnsw.rs:881-888)
+
+
+def test_single_point_at_any_level(pkg):
+    """hnsw.rs:1871-1879 test_sparse_search: one inserted point is found whatever level it drew (distance 0),
+    and its PointId carries that level."""
+    for lvl in (0, 3, 15):
+        h = pkg.Hnsw(16, 10, 16, 50, "DistL1")
+        v = np.arange(8, dtype=np.float32)
+        h.insert_flat(v[None, :], ids=[77], levels=[lvl])
+        o, d, it, pid, cnt = h.search_flat(v[None, :], 3, 10)
+        assert cnt[0] == 1 and o[0, 0] == 77 and d[0, 0] == 0.0 and tuple(pid[0, 0]) == (lvl, 0)
+        assert h.get_max_level_observed() == lvl
+
+
+def test_level_law_and_scale(pkg):
+    """LayerGenerator law (hnsw.rs:363-374) as drawn by the engine: P(level >= 1) = 1/M, and M^-2 after
+    modify_level_scale(0.5) (hnsw.rs:876-905)."""
+    n, M = 60000, 16
+    X = pkg.datagen.uniform(n, 4, 61)
+    for scale, want in ((None, 1.0 / M), (0.5, 1.0 / M ** 2)):
+        h = pkg.Hnsw(M, n, 16, 16, "DistL2")
+        if scale:
+            h.modify_level_scale(scale)
+        h.insert_flat(X)
+        lv = h.export_points()[0]
+        p = (lv >= 1).mean()
+        assert abs(p - want) < 4 * np.sqrt(want / n) + 1e-4, (scale, p, want)
+
+
+def test_row_pointer_entry_points_for_u8(pkg, po):
+    """insert_u8 / parallel_insert_u8 / parallel_search_neighbours_u8 (libext.rs:1052-1116)"""
+    rng = np.random.default_rng(7)
+    X = rng.integers(0, 6, (400, 24)).astype(np.uint8)
+    h = pkg.Hnsw(8, 400, 16, 32, "DistHamming", dtype=np.uint8)
+    h.insert((X[0], 500))
+    h.parallel_insert([(X[i], 500 + i) for i in range(1, 400)])
+    assert h.get_nb_point() == 400
+    par = h.parallel_search([X[3], X[399]], 2, 32)
+    assert par[0][0].d_id == 503 and par[0][0].distance == 0.0 and par[1][0].d_id == 899

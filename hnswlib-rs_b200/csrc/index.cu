@@ -64,6 +64,8 @@ Index::Index(int M_, size_t max_elements_, int max_layer_, int ef_c_, int metric
   }
   own_stream_ = stream_;
   sm_count_ = prop.multiProcessorCount;
+  if (const char* k = getenv("HNSW_B200_KERNEL")) kernel_pref_ = strcmp(k, "warp") == 0 ? 1 : 0;
+  if (const char* k = getenv("HNSW_B200_TVIS_SHIFT")) tvis_scale_shift_ = atoi(k);
   if ((e = cudaMalloc(&d_counter_, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&d_status_, sizeof(int))) != cudaSuccess ||
       (e = cudaMalloc(&d_stats_, 4 * sizeof(unsigned long long))) != cudaSuccess) {
     err_ = std::string("cudaMalloc: ") + cudaGetErrorString(e);
@@ -78,7 +80,7 @@ Index::~Index() {
   if (stream_) cudaStreamSynchronize(stream_);
   cudaFree(d_vec_.p); cudaFree(d_adj0_.p); cudaFree(d_adjU_.p); cudaFree(d_upoff_.p); cudaFree(d_adj0d_.p);
   cudaFree(d_adjUd_.p); cudaFree(d_level_.p); cudaFree(d_plevel_.p); cudaFree(d_origin_.p); cudaFree(d_locks_.p);
-  cudaFree(d_vis_tab_); cudaFree(d_vis_epoch_); cudaFree(d_counter_); cudaFree(d_status_); cudaFree(d_stats_);
+  cudaFree(vis_.tab); cudaFree(vis_.epoch); cudaFree(tvis_.tab); cudaFree(tvis_.epoch); cudaFree(d_counter_); cudaFree(d_status_); cudaFree(d_stats_);
   cudaFree(d_q_); cudaFree(d_out_); cudaFree(d_cnt_); cudaFree(d_fbits_); cudaFree(d_mask_); cudaFree(d_cbuf_);
   if (h_pin_) cudaFreeHost(h_pin_);
   if (h_res_) cudaFreeHost(h_res_);
@@ -141,38 +143,41 @@ int Index::ensure_upper(size_t need) {
   return 0;
 }
 
-int Index::ensure_visited(size_t slots, size_t cap_entries) {
-  if (slots <= vis_slots_ && cap_entries <= vis_cap_) return 0;
-  size_t ns = std::max(slots, vis_slots_), nc = std::max(cap_entries, vis_cap_);
+// A pool is laid out as [slots][cap] for the (slots, cap) it was last sized for.  The warp kernels (insert, filtered and
+// generic search) share one pool; the team kernel owns another, so that its small L2-resident tables are not
+// inflated by the insert path's large ones.
+int Index::ensure_visited(VisitedPool& v, size_t slots, size_t cap_entries) {
+  if (slots <= v.slots && cap_entries <= v.cap) return 0;
+  size_t ns = std::max(slots, v.slots), nc = std::max(cap_entries, v.cap);
   if (ns * nc * sizeof(uint32_t) > ((size_t)8 << 30)) {  // do not carry a huge shape over (filtered searches use few, big tables)
     ns = slots;
     nc = cap_entries;
   }
   HB_CUDA(cudaStreamSynchronize(stream_));
-  cudaFree(d_vis_tab_);
-  cudaFree(d_vis_epoch_);
-  d_vis_tab_ = d_vis_epoch_ = nullptr;
-  vis_slots_ = vis_cap_ = 0;
-  HB_CUDA(cudaMalloc(&d_vis_tab_, ns * nc * sizeof(uint32_t)));
-  HB_CUDA(cudaMalloc(&d_vis_epoch_, ns * sizeof(uint32_t)));
-  HB_CUDA(cudaMemsetAsync(d_vis_tab_, 0, ns * nc * sizeof(uint32_t), stream_));
+  cudaFree(v.tab);
+  cudaFree(v.epoch);
+  v.tab = v.epoch = nullptr;
+  v.slots = v.cap = 0;
+  HB_CUDA(cudaMalloc(&v.tab, ns * nc * sizeof(uint32_t)));
+  HB_CUDA(cudaMalloc(&v.epoch, ns * sizeof(uint32_t)));
+  HB_CUDA(cudaMemsetAsync(v.tab, 0, ns * nc * sizeof(uint32_t), stream_));
   // epoch = max forces a table clear on first use whatever id_bits is (Visited::begin)
-  HB_CUDA(cudaMemsetAsync(d_vis_epoch_, 0xFF, ns * sizeof(uint32_t), stream_));
-  vis_slots_ = ns;
-  vis_cap_ = nc;
+  HB_CUDA(cudaMemsetAsync(v.epoch, 0xFF, ns * sizeof(uint32_t), stream_));
+  v.slots = ns;
+  v.cap = nc;
   return 0;
 }
 
-int Index::fill_visited_cfg(VisitedCfg& c) {
+int Index::fill_visited_cfg(VisitedPool& v, VisitedCfg& c) {
   const int id_bits = std::max(1, ilog2(std::max<size_t>(cap_, 2)));
-  if (id_bits != vis_id_bits_) {  // entries are (epoch << id_bits) | id: a new split invalidates every table
-    HB_CUDA(cudaMemsetAsync(d_vis_epoch_, 0xFF, vis_slots_ * sizeof(uint32_t), stream_));
-    vis_id_bits_ = id_bits;
+  if (id_bits != v.id_bits) {  // entries are (epoch << id_bits) | id: a new split invalidates every table
+    HB_CUDA(cudaMemsetAsync(v.epoch, 0xFF, v.slots * sizeof(uint32_t), stream_));
+    v.id_bits = id_bits;
   }
-  c.tables = d_vis_tab_;
-  c.epochs = d_vis_epoch_;
-  c.cap = (uint32_t)vis_cap_;
-  c.shift = 32 - ilog2(vis_cap_);
+  c.tables = v.tab;
+  c.epochs = v.epoch;
+  c.cap = (uint32_t)v.cap;
+  c.shift = 32 - ilog2(v.cap);
   c.id_bits = id_bits;
   return 0;
 }
@@ -270,8 +275,8 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
   size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)2 * (ef_c + 16) * p.g.deg0));
   for (int attempt = 0;; ++attempt) {
     int r;
-    if ((r = ensure_visited((size_t)grid * wpb, vcap))) return r;
-    if ((r = fill_visited_cfg(p.vis))) return r;
+    if ((r = ensure_visited(vis_, (size_t)grid * wpb, vcap))) return r;
+    if ((r = fill_visited_cfg(vis_, p.vis))) return r;
     HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
     HB_CUDA(launch_insert_search(p, metric, dtype, grid, smem, stream_, false, nullptr));
     int status = 0;
@@ -280,7 +285,7 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
     if (status == 0) break;
     if (attempt >= 8) return fail("visited table overflow persists");
     HB_CUDA(cudaMemsetAsync(d_status_, 0, sizeof(int), stream_));
-    vcap = vis_cap_ * 2;  // rare: a search wandered further than 2*(ef+16)*degree nodes
+    vcap = vis_.cap * 2;  // rare: a search wandered further than 2*(ef+16)*degree nodes
   }
   int lgrid = (int)std::min<size_t>((size_t)sm_count_ * 8, (count + wpb - 1) / wpb);
   HB_CUDA(launch_insert_link(p, lgrid, stream_));
@@ -525,50 +530,62 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
   p.stats = stats_on_ ? d_stats_ : nullptr;
   p.status = d_status_;
   const bool filtered = d_filter_bits != nullptr;
-  p.q_kind = filtered ? 0 : queue_kind(p.ef, metric, dtype);
-  p.q_smem = queue_slots(p.q_kind, p.ef);
-  size_t spw = search_smem_per_warp(p.g.d4, p.q_smem);
+  // kernel choice: the team kernel (8 lanes per query, search_team.cu) whenever it applies, else one warp per query
+  const bool team = !filtered && kernel_pref_ != 1 && entry != INVALID_ID && team_op_supported(metric, dtype) &&
+                    team_eligible(p.g.d4, p.ef);
+  p.q_kind = (filtered || team) ? 0 : queue_kind(p.ef, metric, dtype);
+  p.q_smem = team ? team_queue_slots(p.ef) : queue_slots(p.q_kind, p.ef);
+  size_t spw = team ? 4 * team_smem_per_team(p.g.d4, p.q_smem) : search_smem_per_warp(p.g.d4, p.q_smem);
   p.smem_per_warp = (int)spw;
-  const int wpb = SEARCH_THREADS / 32;
+  const int wpb = (team ? TEAM_THREADS : SEARCH_THREADS) / 32;
+  const int qpw = team ? 4 : 1;  // queries in flight per warp
   const size_t smem = spw * wpb;
   if (smem > 220 * 1024) return fail("ef / dimension too large for the search kernel's shared memory");
   p.cbuf = nullptr;
   p.ccap = 0;
   int bps = 0;
   {
-    const auto key = std::make_tuple((int)filtered, p.q_kind, p.g.d4, smem);
+    const auto key = std::make_tuple(team ? 2 : (int)filtered, team ? p.q_smem : p.q_kind, p.g.d4, smem);
     auto it = occ_cache_.find(key);
     if (it != occ_cache_.end()) {
       bps = it->second;
     } else {
-      if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, 0, smem, stream_, true, &bps));
+      if (team) HB_CUDA(launch_search_team(p, metric, dtype, 0, smem, stream_, true, &bps));
+      else if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, 0, smem, stream_, true, &bps));
       else HB_CUDA(launch_search(p, metric, dtype, 0, smem, stream_, true, &bps));
       occ_cache_[key] = bps;
     }
   }
   if (bps < 1) return fail("search kernel does not fit on an SM");
-  int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (nq + wpb - 1) / wpb);
+  const size_t per_cta = (size_t)wpb * qpw;
+  int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (nq + per_cta - 1) / per_cta);
   const int deg = layer0 == 0 ? 2 * M : M;
-  size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)2 * (p.ef + 16) * deg));
+  // visited-table capacity per query slot.  A search inserts ~ (ef + a few) * (fresh neighbours per expansion) ids; the
+  // tables are meant to stay in L2, so the team kernel (2-4x more slots in flight) starts from half the warp kernel's
+  // size.  An overflow is detected in the kernel and the batch re-run with doubled tables.
+  size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)(team ? 1 : 2) * (p.ef + 16) * deg));
+  if (team && tvis_scale_shift_ != 0) vcap = tvis_scale_shift_ > 0 ? vcap << tvis_scale_shift_ : std::max<size_t>(1024, vcap >> -tvis_scale_shift_);
+  VisitedPool& pool = team ? tvis_ : vis_;
   for (int attempt = 0;; ++attempt) {
     int r;
     if (filtered) {
       // a filtered search keeps expanding until its candidate queue is empty (hnsw.rs:992-1001) and may visit the
       // whole graph: keep (visited table + candidate queue) under ~6 GB by running fewer warps when tables are big
-      const size_t per_slot = std::max(vcap, vis_cap_) * 12;
+      const size_t per_slot = std::max(vcap, pool.cap) * 12;
       const size_t max_slots = std::max<size_t>(wpb, ((size_t)6 << 30) / per_slot);
       grid = (int)std::max<size_t>(1, std::min<size_t>(grid, max_slots / wpb));
     }
-    if ((r = ensure_visited((size_t)grid * wpb, vcap))) return r;
-    if ((r = fill_visited_cfg(p.vis))) return r;
+    if ((r = ensure_visited(pool, (size_t)grid * per_cta, vcap))) return r;
+    if ((r = fill_visited_cfg(pool, p.vis))) return r;
     if (filtered) {
-      if ((r = ensure_scratch(&d_cbuf_, &d_cbuf_bytes_, (size_t)grid * wpb * vis_cap_ * 8))) return r;
+      if ((r = ensure_scratch(&d_cbuf_, &d_cbuf_bytes_, (size_t)grid * wpb * pool.cap * 8))) return r;
       p.cbuf = (uint64_t*)d_cbuf_;
-      p.ccap = (uint32_t)vis_cap_;
+      p.ccap = (uint32_t)pool.cap;
     }
     HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
     HB_CUDA(cudaEventRecord(ev0_, stream_));
-    if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, grid, smem, stream_, false, nullptr));
+    if (team) HB_CUDA(launch_search_team(p, metric, dtype, grid, smem, stream_, false, nullptr));
+    else if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, grid, smem, stream_, false, nullptr));
     else HB_CUDA(launch_search(p, metric, dtype, grid, smem, stream_, false, nullptr));
     HB_CUDA(cudaEventRecord(ev1_, stream_));
     if (!sync) break;
@@ -581,7 +598,7 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
     }
     if (attempt >= 24) return fail("visited table overflow persists");
     HB_CUDA(cudaMemsetAsync(d_status_, 0, sizeof(int), stream_));
-    vcap = vis_cap_ * 2;
+    vcap = pool.cap * 2;
   }
   stat_queries_ += stats_on_ ? nq : 0;
   return 0;

@@ -125,7 +125,14 @@ class Index {
   int cuda_fail(cudaError_t e, const char* what) const;
   int ensure_points(size_t need);
   int ensure_upper(size_t need_lists);
-  int ensure_visited(size_t slots, size_t cap_entries);
+  struct VisitedPool {
+    uint32_t* tab = nullptr;
+    uint32_t* epoch = nullptr;
+    size_t slots = 0, cap = 0;
+    int id_bits = 0;
+  };
+  int ensure_visited(VisitedPool& v, size_t slots, size_t cap_entries);
+  int fill_visited_cfg(VisitedPool& v, VisitedCfg& c);
   int ensure_scratch(void** p, size_t* cur, size_t need);
   int grow_plevel(uint32_t id, int new_plevel);
   int run_insert_range(size_t first, size_t count, const std::vector<uint16_t>& masks, size_t mask_off);
@@ -146,12 +153,10 @@ class Index {
   DevArray<uint64_t> d_origin_;
   DevArray<int> d_locks_;
 
-  // visited tables
-  uint32_t* d_vis_tab_ = nullptr;
-  uint32_t* d_vis_epoch_ = nullptr;
-  size_t vis_slots_ = 0, vis_cap_ = 0;
-  int vis_id_bits_ = 0;
-  int fill_visited_cfg(VisitedCfg& c);
+  // visited tables: vis_ serves the warp-per-query kernels, tvis_ the team kernel
+  VisitedPool vis_, tvis_;
+  int kernel_pref_ = 0;        // 0 = automatic, 1 = never use the team kernel (env HNSW_B200_KERNEL=warp; A/B measurements)
+  int tvis_scale_shift_ = 0;   // env HNSW_B200_TVIS_SHIFT: scale the team kernel's visited tables by 2^shift (measurements)
 
   // small device scratch
   unsigned int* d_counter_ = nullptr;

@@ -13,6 +13,8 @@ inline int dtype_size(int dt) { return dt == DT_U8 ? 1 : dt == DT_U16 ? 2 : 4; }
 
 constexpr int SEARCH_THREADS = 256;  // 8 warps = 8 queries in flight per CTA
 constexpr int BUILD_THREADS = 128;   // 4 warps = 4 inserts in flight per CTA
+constexpr int TEAM_THREADS = 32;     // team kernel (search_team.cu): one warp per CTA = 4 queries of 8 lanes each
+constexpr int TEAM_MIN_BLOCKS = 16;  // 16 warps x 4 teams = 64 queries resident per SM, <= 128 registers per thread
 
 // One answer slot.  Same 16-byte layout as the reference's #[repr(C)] Neighbour_api {id: usize, d: f32}
 // (/root/reference/src/libext.rs:64-71); the internal id rides in what is tail padding there.
@@ -65,6 +67,15 @@ inline size_t search_smem_per_warp(int d4, int q_smem) {
   return (b + 127) & ~(size_t)127;
 }
 
+// ---- team kernel (search_team.cu): eligibility and shared-memory footprint
+// rows of 128 / 256 / 512 bytes (compile-time chunk count), ef <= 128, no filter
+inline int team_queue_slots(int ef) { return ef <= 64 ? 64 : (ef <= 128 ? 128 : 0); }
+inline bool team_eligible(int d4, int ef) { return (d4 == 8 || d4 == 16 || d4 == 32) && team_queue_slots(ef) != 0; }
+inline size_t team_smem_per_team(int d4, int qc) {
+  const size_t ub = (size_t)d4 * 16 > (size_t)qc * 8 ? (size_t)d4 * 16 : (size_t)qc * 8;
+  return ub + 128;
+}
+
 struct InsertParams {
   GraphView g;
   uint32_t first;   // internal id of the first point of the batch
@@ -96,6 +107,8 @@ cudaError_t launch_search_filtered(const SearchParams& p, int metric, int dtype,
                                    bool query_only, int* blocks_per_sm);
 cudaError_t launch_search(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st, bool query_only,
                           int* blocks_per_sm);
+cudaError_t launch_search_team(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
+                               bool query_only, int* blocks_per_sm);
 
 // ---- (metric, element type) -> distance functor.  f is called as f(OpTag<Op>{}) and returns cudaError_t.
 template <class Op>
@@ -111,6 +124,15 @@ template <> struct Specialise<OpL1> { static constexpr bool value = true; };
 template <> struct Specialise<OpL2> { static constexpr bool value = true; };
 template <> struct Specialise<OpDot> { static constexpr bool value = true; };
 template <> struct Specialise<OpCosine> { static constexpr bool value = true; };
+
+// ops the team kernel (search_team.cu) is instantiated for
+template <class Op>
+struct TeamOp {
+  static constexpr bool value = Specialise<Op>::value;
+};
+inline bool team_op_supported(int metric, int dtype) {
+  return dtype == DT_F32 && (metric == METRIC_L1 || metric == METRIC_L2 || metric == METRIC_DOT || metric == METRIC_COSINE);
+}
 
 template <class T, class F>
 cudaError_t dispatch_int(int metric, bool with_jaccard, F&& f) {

@@ -1,0 +1,528 @@
+// Query kernel, team form: EIGHT lanes own one query, four queries ride one warp.
+//
+// Restates /root/reference/src/hnsw.rs:1487-1580 (search_filter without a filter: entry fetch, one hop per
+// upper layer, search_layer on the lowest populated layer, ascending top-k) and hnsw.rs:922-1064 (search_layer),
+// with the batch contract of parallel_search (hnsw.rs:1612-1635: one answer per query, in input order).
+//
+// Why teams.  A point row is read by 8 lanes x 16 bytes whatever the kernel shape, so in the warp-per-query kernel
+// (search.cu) 24 of 32 lanes idle through all the per-query bookkeeping: picking the next candidate, marking it,
+// queue inserts, the loop control.  Here the four teams of a warp run the SAME instruction stream on four queries:
+// every warp instruction that used to serve one query serves four, a 10 000-query batch is resident at once
+// (148 SMs x 16 warps x 4 = 9472 teams) so nothing waits for a second wave, and what remains is the row traffic.
+//
+// A team is a small state machine; one loop iteration is one STEP = "score up to 32 rows named by one chunk of one
+// adjacency list":
+//   FETCH   take a query index, stage the query, registers <- the lane's 16-byte chunks of it
+//   DESC    layer entry_level+1: score the entry point; layers entry_level..1: score pivot.neighbours[layer],
+//           strict '<' first minimum becomes the pivot (hnsw.rs:1511-1529)
+//   SEARCH  pop the nearest unexpanded entry of W, read its list, drop visited ids, score the rest, insert
+//           (hnsw.rs:969-1057)
+// The scoring part (the row gather, the only heavy part) is common code all four teams execute together whatever
+// their states; the state-specific parts before and after it are short.
+//
+// Queue: W is a sorted array of (dist,id) keys in shared memory, 8 lanes wide; which entries are still unexpanded
+// (the reference's C, see search_core.cuh) is a bit mask in registers, so "pop nearest candidate" is a find-first-set.
+// Visited set: the per-slot epoch-tagged table of common.cuh, probed four ids per lane, claimed with atomicCAS.
+// Distances: identical lane/chunk mapping and reduction tree as warp_dists (bit-identical results); the 8-lane
+// reduction of four rows is done as one transposed reduction (4+2+1 shuffles instead of 4 x 3).
+#include "kernels.h"
+
+namespace hb {
+
+enum : int { TS_FETCH = 0, TS_DESC = 1, TS_SEARCH = 2, TS_DONE = 3 };
+
+// ---- reduction arithmetic of the Ops' partial sums, by type (same operations as every Op::comb)
+__device__ __forceinline__ float radd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ uint32_t radd(uint32_t a, uint32_t b) { return a + b; }
+__device__ __forceinline__ Cos3 radd(const Cos3& a, const Cos3& b) {
+  return Cos3{__dadd_rn(a.ab, b.ab), __dadd_rn(a.aa, b.aa), __dadd_rn(a.bb, b.bb)};
+}
+__device__ __forceinline__ MinMax64 radd(const MinMax64& a, const MinMax64& b) { return MinMax64{a.mn + b.mn, a.mx + b.mx}; }
+__device__ __forceinline__ float rshfl(float a, int off) { return __shfl_xor_sync(FULL, a, off); }
+__device__ __forceinline__ uint32_t rshfl(uint32_t a, int off) { return __shfl_xor_sync(FULL, a, off); }
+__device__ __forceinline__ Cos3 rshfl(const Cos3& a, int off) {
+  return Cos3{__shfl_xor_sync(FULL, a.ab, off), __shfl_xor_sync(FULL, a.aa, off), __shfl_xor_sync(FULL, a.bb, off)};
+}
+__device__ __forceinline__ MinMax64 rshfl(const MinMax64& a, int off) {
+  return MinMax64{__shfl_xor_sync(FULL, a.mn, off), __shfl_xor_sync(FULL, a.mx, off)};
+}
+
+// Four rows' per-lane partial sums -> the finished value of row (g >> 1) in lane g, over the team's 8 lanes.
+// Same pairing as reduce8's xor butterfly (4, 2, 1): a lane adds its own partial and the partner's, so every sum has
+// the operands of the butterfly (IEEE addition is commutative): bit-identical.
+template <class R>
+__device__ __forceinline__ R treduce4(const R& a0, const R& a1, const R& a2, const R& a3, int g) {
+  const bool h4 = (g & 4) != 0;
+  const R b0 = radd(h4 ? a2 : a0, rshfl(h4 ? a0 : a2, 4));
+  const R b1 = radd(h4 ? a3 : a1, rshfl(h4 ? a1 : a3, 4));
+  const bool h2 = (g & 2) != 0;
+  R c = radd(h2 ? b1 : b0, rshfl(h2 ? b0 : b1, 2));
+  c = radd(c, rshfl(c, 1));
+  return c;
+}
+
+// ---- the "still unexpanded" mask over queue positions: bit p set <=> W[p] has not been expanded yet
+struct Mask64 {
+  uint64_t m;
+  __device__ __forceinline__ void clear() { m = 0; }
+  __device__ __forceinline__ bool none() const { return m == 0; }
+  __device__ __forceinline__ int first() const { return __ffsll((long long)m) - 1; }  // -1 when none
+  __device__ __forceinline__ void drop_first() { m &= m - 1; }
+  __device__ __forceinline__ void set_only(int p) { m = 1ull << p; }
+  // a key enters the queue at position p: entries at >= p move up by one, the bit beyond `cap` entries falls off
+  __device__ __forceinline__ void insert_at(int p, int cap) {
+    const uint64_t low = (1ull << p) - 1ull;
+    m = (m & low) | (1ull << p) | ((m & ~low) << 1);
+    if (cap < 64) m &= (1ull << cap) - 1ull;
+  }
+};
+struct Mask128 {
+  uint64_t lo, hi;
+  __device__ __forceinline__ void clear() { lo = hi = 0; }
+  __device__ __forceinline__ bool none() const { return (lo | hi) == 0; }
+  __device__ __forceinline__ int first() const {
+    return lo ? __ffsll((long long)lo) - 1 : (hi ? 63 + __ffsll((long long)hi) : -1);
+  }
+  __device__ __forceinline__ void drop_first() {
+    if (lo) lo &= lo - 1;
+    else hi &= hi - 1;
+  }
+  __device__ __forceinline__ void set_only(int p) {
+    lo = p < 64 ? 1ull << p : 0ull;
+    hi = p < 64 ? 0ull : 1ull << (p - 64);
+  }
+  __device__ __forceinline__ void insert_at(int p, int cap) {
+    const uint64_t carry = lo >> 63;
+    if (p < 64) {
+      const uint64_t low = (1ull << p) - 1ull;
+      lo = (lo & low) | (1ull << p) | ((lo & ~low) << 1);
+      hi = (hi << 1) | carry;
+    } else {
+      const int q = p - 64;
+      const uint64_t low = (1ull << q) - 1ull;
+      hi = (hi & low) | (1ull << q) | ((hi & ~low) << 1);
+    }
+    if (cap < 128) {
+      if (cap <= 64) {
+        hi = 0;
+        if (cap < 64) lo &= (1ull << cap) - 1ull;
+      } else {
+        hi &= (1ull << (cap - 64)) - 1ull;
+      }
+    }
+  }
+};
+template <int QC>
+struct MaskSel;
+template <> struct MaskSel<64> { typedef Mask64 type; };
+template <> struct MaskSel<128> { typedef Mask128 type; };
+
+__device__ __forceinline__ uint32_t atom_cas_keep(uint32_t* p, uint32_t cmp, uint32_t val, uint64_t pol) {
+  (void)pol;  // ptxas (12.9) rejects .L2::cache_hint on atom.cas; the probe loads carry the policy
+  return atomicCAS(p, cmp, val);
+}
+
+// copy one query row into the team's staging buffer, zero padded to row_bytes (8 lanes; cf. stage_row_bytes)
+__device__ __forceinline__ void team_stage_row(void* dst, const void* src, int nbytes, int row_bytes, int g, unsigned tmask) {
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+  const int nw = nbytes >> 2;
+  if ((reinterpret_cast<size_t>(src) & 3) == 0) {
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+    for (int i = g; i < (row_bytes >> 2); i += 8) d32[i] = i < nw ? s32[i] : 0u;
+    __syncwarp(tmask);
+    const uint8_t* s8 = reinterpret_cast<const uint8_t*>(src);
+    uint8_t* d8 = reinterpret_cast<uint8_t*>(dst);
+    for (int i = (nw << 2) + g; i < nbytes; i += 8) d8[i] = s8[i];
+  } else {
+    const uint8_t* s8 = reinterpret_cast<const uint8_t*>(src);
+    uint8_t* d8 = reinterpret_cast<uint8_t*>(dst);
+    for (int i = g; i < row_bytes; i += 8) d8[i] = i < nbytes ? s8[i] : (uint8_t)0;
+  }
+  __syncwarp(tmask);
+}
+
+// 4 consecutive ids of a list per lane (ids 4g..4g+3 of the 32-id chunk at `base`), INVALID_ID beyond the capacity
+__device__ __forceinline__ void load_ids4(const uint32_t* ids, int lcap, int base, int g, uint32_t (&nid)[4]) {
+  const int o = base + 4 * g;
+  if (ids != nullptr && (lcap & 3) == 0 && o + 3 < lcap) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(ids + o));
+    nid[0] = v.x; nid[1] = v.y; nid[2] = v.z; nid[3] = v.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) nid[j] = (ids != nullptr && o + j < lcap) ? __ldg(ids + o + j) : INVALID_ID;
+  }
+}
+
+// CH = 16-byte chunks per lane per row (row = CH * 128 bytes), QC = queue slots (>= ef)
+template <class Op, int CH, int QC>
+__global__ void __launch_bounds__(TEAM_THREADS, TEAM_MIN_BLOCKS) search_team_kernel(SearchParams p) {
+  typedef typename MaskSel<QC>::type MaskT;
+  typedef typename Op::red_t red_t;
+  constexpr int UB = (CH * 128 > QC * 8) ? CH * 128 : QC * 8;  // query staging and the queue share one buffer
+  constexpr int BL = QC / 8;                                   // queue entries per lane block
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int team = lane >> 3, g = lane & 7, tl0 = lane & 24;
+  const unsigned tmask = 0xFFu << tl0;
+  const GraphView& G = p.g;
+  unsigned char* tb = smem_raw + (size_t)(warp * 4 + team) * (UB + 128);
+  uint64_t* w = reinterpret_cast<uint64_t*>(tb);
+  uint4* qs = reinterpret_cast<uint4*>(tb);
+  uint32_t* cand = reinterpret_cast<uint32_t*>(tb + UB);
+  const uint4* vec4 = reinterpret_cast<const uint4*>(G.vec);
+  const uint64_t pol_rows = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+
+  // ---- visited table of this team (Visited of common.cuh, 8 lanes wide)
+  const uint32_t slot = (blockIdx.x * (TEAM_THREADS / 32) + warp) * 4 + team;
+  uint32_t* const vtab = p.vis.tables + (size_t)slot * p.vis.cap;
+  const uint32_t vmask = p.vis.cap - 1, vlimit = p.vis.cap - (p.vis.cap >> 2);
+  const int vshift = p.vis.shift, id_bits = p.vis.id_bits;
+  const uint32_t epoch_max = (id_bits >= 32) ? 0u : ((1u << (32 - id_bits)) - 1u);
+  uint32_t epoch = p.vis.epochs[slot], vtag = 0, vused = 0;
+
+  uint4 qv[CH];
+  int state = TS_FETCH, layer = 0, base = 0, n = 0;
+  uint32_t qi = 0, cur = INVALID_ID, newpiv = INVALID_ID;
+  float best = 0.f;
+  MaskT open;
+  open.clear();
+  uint64_t thr = ~0ull;
+  unsigned evals = 0, expans = 0, adjr = 0;
+  bool overflow = false;
+  const int cap = p.ef;
+
+  for (;;) {
+    // ================================================================ completion: ascending top-k (hnsw.rs:1544-1579)
+    if (state == TS_SEARCH && base == 0 && (open.none() || overflow)) {
+      int count = n < p.k ? n : p.k;  // hnsw.rs:1547 (n <= ef)
+      if (overflow) {
+        if (g == 0) atomicExch(p.status, 1);
+        count = 0;
+      }
+      const size_t ob = (size_t)qi * p.k;
+      for (int j = g; j < p.k; j += 8) {
+        if (j < count) {
+          const uint64_t key = w[j];
+          const uint32_t id = key_id(key);
+          p.out_nb[ob + j] = NeighbourOut{G.origin[id], key_dist(key), id};
+        } else {
+          p.out_nb[ob + j] = NeighbourOut{~0ull, __int_as_float(0x7f800000), INVALID_ID};
+        }
+      }
+      if (g == 0) p.out_count[qi] = count;
+      __syncwarp(tmask);  // the queue is read before FETCH reuses the buffer
+      overflow = false;
+      state = TS_FETCH;
+    }
+    // ================================================================ FETCH
+    if (state == TS_FETCH) {
+      uint32_t q = 0;
+      if (g == 0) q = atomicAdd(p.work_counter, 1u);
+      q = __shfl_sync(tmask, q, tl0);
+      if (q >= p.nq) {
+        state = TS_DONE;
+      } else {
+        qi = q;
+        team_stage_row(qs, reinterpret_cast<const char*>(p.queries) + (size_t)qi * p.q_stride_bytes, p.q_bytes, CH * 128, g, tmask);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) qv[i] = qs[g + 8 * i];
+        __syncwarp(tmask);
+        cur = newpiv = G.entry;  // hnsw.rs:1498-1506
+        best = __int_as_float(0x7f800000);
+        layer = G.entry_level + 1;  // "layer" above the top: the step that scores the entry point itself
+        base = 0;
+        state = TS_DESC;
+      }
+    }
+    if (__all_sync(FULL, state == TS_DONE)) break;
+
+    // ================================================================ the step's row list
+    int n_t = 0;
+    bool more = false;
+    if (state == TS_DESC) {
+      if (layer > G.entry_level) {
+        if (g == 0) cand[0] = cur;
+        n_t = 1;
+        evals += 1;
+      } else {  // one pass over pivot.neighbours[layer] (hnsw.rs:1511-1529), 32 ids per step
+        int lcap;
+        const uint32_t* ids = list_ids(G, cur, layer, lcap);
+        uint32_t nid[4];
+        load_ids4(ids, lcap, base, g, nid);
+        const int mine = (nid[0] != INVALID_ID) + (nid[1] != INVALID_ID) + (nid[2] != INVALID_ID) + (nid[3] != INVALID_ID);
+        const int fl = __popc(__ballot_sync(tmask, mine == 4));  // lists are dense prefixes
+        n_t = 4 * fl + __shfl_sync(tmask, mine, tl0 + (fl & 7)) * (fl < 8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (nid[j] != INVALID_ID) cand[4 * g + j] = nid[j];
+        evals += n_t;
+        adjr += n_t;
+        more = (n_t == 32) && (base + 32 < lcap);
+      }
+      __syncwarp(tmask);
+    } else if (state == TS_SEARCH) {
+      if (base == 0) {  // C.pop(): the nearest unexpanded entry of W (hnsw.rs:971); the stop rule is "none left"
+        const int idx = open.first();
+        open.drop_first();
+        cur = key_id(w[idx]);
+        expans += 1;
+        // pull the adjacency rows of the next two candidates towards L2 while this one is expanded
+        MaskT o2 = open;
+        if (g == 2) o2.drop_first();
+        if ((g == 1 || g == 2) && !o2.none()) {
+          const uint32_t pc = key_id(w[o2.first()]);
+          int pcap;
+          const uint32_t* pids = list_ids(G, pc, p.layer0, pcap);
+          if (pids) asm volatile("prefetch.global.L2 [%0];" ::"l"(pids));
+        }
+      }
+      int lcap;
+      const uint32_t* ids = list_ids(G, cur, p.layer0, lcap);  // hnsw.rs:1006
+      uint32_t nid[4];
+      load_ids4(ids, lcap, base, g, nid);
+      const int mine = (nid[0] != INVALID_ID) + (nid[1] != INVALID_ID) + (nid[2] != INVALID_ID) + (nid[3] != INVALID_ID);
+      const int fl = __popc(__ballot_sync(tmask, mine == 4));
+      const int nvalid = 4 * fl + __shfl_sync(tmask, mine, tl0 + (fl & 7)) * (fl < 8);
+      adjr += nvalid;
+      more = (nvalid == 32) && (base + 32 < lcap);
+      // ---- visited test-and-set of the lane's (up to) four ids (hnsw.rs:1016-1017)
+      uint32_t h[4];
+      bool pend[4], fresh[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = (nid[j] * 2654435761u) >> vshift;
+        pend[j] = nid[j] != INVALID_ID;
+        fresh[j] = false;
+      }
+      while (__any_sync(tmask, pend[0] | pend[1] | pend[2] | pend[3])) {
+        uint32_t cv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cv[j] = pend[j] ? ld_keep(vtab + h[j], pol_keep) : 0u;
+        bool claim[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t want = vtag | nid[j];
+          claim[j] = false;
+          if (pend[j]) {
+            if (cv[j] == want) pend[j] = false;                      // already visited
+            else if ((cv[j] >> id_bits) != epoch) claim[j] = true;   // stale or empty slot
+            else h[j] = (h[j] + 1) & vmask;
+          }
+        }
+        uint32_t old[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) old[j] = claim[j] ? atom_cas_keep(vtab + h[j], cv[j], vtag | nid[j], pol_keep) : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (claim[j]) {
+            if (old[j] == cv[j]) {
+              fresh[j] = true;
+              pend[j] = false;
+            } else if (old[j] == (vtag | nid[j])) {
+              pend[j] = false;  // the same id twice in one chunk: its first occurrence recorded it
+            } else {
+              h[j] = (h[j] + 1) & vmask;  // another id of this chunk took the slot
+            }
+          }
+        }
+      }
+      // ---- compact the fresh ids into the team's row list
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned fb = (__ballot_sync(tmask, fresh[j]) >> tl0) & 0xFFu;
+        if (fresh[j]) cand[n_t + __popc(fb & ((1u << g) - 1u))] = nid[j];
+        n_t += __popc(fb);
+      }
+      vused += n_t;
+      evals += n_t;
+      __syncwarp(tmask);
+    }
+
+    // ================================================================ scoring: rows cand[0..n_t) of every team, 4 per block
+    const int maxn = __reduce_max_sync(FULL, n_t);
+    const int nblk = (maxn + 3) >> 2;
+    uint64_t dkey = ~0ull;  // DESC: smallest (distance, list position) seen by this lane
+    uint4 x[4][CH];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (u < n_t) {
+        const uint4* row = vec4 + (size_t)cand[u] * G.d4 + g;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) x[u][i] = ldg_stream(row + 8 * i, pol_rows);
+      }
+    }
+    for (int b = 0; b < nblk; ++b) {
+      red_t a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        typename Op::acc_t acc = Op::zero();
+#pragma unroll
+        for (int i = 0; i < CH; ++i) Op::chunk(acc, qv[i], x[u][i]);
+        a[u] = Op::fold(acc);
+      }
+      if (b + 1 < nblk) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = 4 * (b + 1) + u;
+          if (r < n_t) {
+            const uint4* row = vec4 + (size_t)cand[r] * G.d4 + g;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) x[u][i] = ldg_stream(row + 8 * i, pol_rows);
+          }
+        }
+      }
+      const red_t tot = treduce4<red_t>(a[0], a[1], a[2], a[3], g);
+      const float dist = Op::post(Op::finish(tot, G.dim));  // hnsw.rs:1026 / 1518
+      const int r = 4 * b + (g >> 1);
+      const bool has = r < n_t;
+      uint64_t key = ~0ull;
+      if (has) {
+        if (state == TS_DESC) {
+          key = ((uint64_t)__float_as_uint(dist) << 32) | (uint32_t)r;
+          dkey = key < dkey ? key : dkey;
+        } else {
+          key = make_key(dist, cand[r]);
+        }
+      }
+      // ---- SEARCH: W and C updates (hnsw.rs:1028-1053), one accepted candidate per team per round
+      unsigned tbits = (__ballot_sync(FULL, state == TS_SEARCH && has && (g & 1) == 0 && key < thr) >> tl0) & 0xFFu;
+      while (__any_sync(FULL, tbits != 0)) {
+        const bool act0 = tbits != 0;
+        const int src = tl0 + (act0 ? __ffs(tbits) - 1 : 0);
+        tbits &= tbits - 1;
+        const uint64_t kj = __shfl_sync(FULL, key, src);
+        const bool act = act0 && kj < thr;  // the bound may have tightened since the ballot
+        // position = number of keys below kj: the lane blocks wholly below, then inside the first block that is not
+        const unsigned b1 = (__ballot_sync(FULL, act && w[BL * g + BL - 1] < kj) >> tl0) & 0xFFu;
+        const int nb = __popc(b1) & 7;
+        int pos = BL * nb;
+#pragma unroll
+        for (int t = 0; t < BL; t += 8) {
+          const int i = BL * nb + t + g;
+          const bool in = (BL >= 8) || (g < BL);
+          pos += __popc((__ballot_sync(FULL, act && in && w[in ? i : 0] < kj) >> tl0) & 0xFFu);
+        }
+        // shift [pos, hi] up by one (the last entry of a full queue drops out), 16 entries per round, top down
+        const int lo = act ? pos : 0x7fffffff;
+        int top = (n < cap ? n : cap - 1) - 1;
+        while (__any_sync(FULL, top >= lo)) {
+          const int i0 = top - g, i1 = top - 8 - g;
+          uint64_t v0 = 0, v1 = 0;
+          if (i0 >= lo) v0 = w[i0];
+          if (i1 >= lo) v1 = w[i1];
+          __syncwarp();
+          if (i0 >= lo) w[i0 + 1] = v0;
+          if (i1 >= lo) w[i1 + 1] = v1;
+          __syncwarp();
+          top -= 16;
+        }
+        if (act && g == 0) w[pos] = kj;
+        __syncwarp();
+        if (act) {
+          n = n < cap ? n + 1 : cap;
+          thr = w[cap - 1];
+          open.insert_at(pos, cap);
+        }
+      }
+    }
+
+    // ================================================================ after the step
+    if (state == TS_DESC) {
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const uint64_t other = __shfl_xor_sync(tmask, dkey, o);
+        dkey = other < dkey ? other : dkey;
+      }
+      const float dmin = __uint_as_float((uint32_t)(dkey >> 32));
+      if (n_t > 0 && dmin < best) {  // strict '<' in list order == the first minimum, if below `best`
+        best = dmin;
+        newpiv = cand[(uint32_t)dkey & 31u];
+      }
+      __syncwarp(tmask);  // cand is read before the next step rewrites it
+      if (more) {
+        base += 32;
+      } else {
+        base = 0;
+        cur = newpiv;  // hnsw.rs:1526-1528
+        layer -= 1;
+        if (layer < 1) {
+          // ---- search_layer on the lowest populated layer starts (hnsw.rs:1531-1542, 940-967)
+          if (epoch >= epoch_max) {
+            for (uint32_t i = g; i <= vmask; i += 8) vtab[i] = 0u;
+            epoch = 0;
+          }
+          epoch += 1;
+          vtag = epoch << id_bits;
+          vused = 1;
+#pragma unroll
+          for (int t = 0; t < BL; ++t) w[g + 8 * t] = ~0ull;
+          __syncwarp(tmask);
+          if (g == 0) {
+            w[0] = make_key(best, cur);  // the entry of the layer enters W and C
+            st_keep(vtab + ((cur * 2654435761u) >> vshift), vtag | cur, pol_keep);
+          }
+          __syncwarp(tmask);
+          evals += 1;  // search_layer's own evaluation of its entry point (hnsw.rs:952): the value is `best`
+          n = 1;
+          open.set_only(0);
+          thr = w[cap - 1];
+          state = TS_SEARCH;
+        }
+      }
+    } else if (state == TS_SEARCH) {
+      __syncwarp(tmask);
+      if (vused >= vlimit) {
+        overflow = true;
+        base = 0;
+      } else {
+        base = more ? base + 32 : 0;
+      }
+    }
+  }
+
+  if (g == 0) {
+    p.vis.epochs[slot] = epoch;
+    if (p.stats) {
+      atomicAdd(p.stats + 0, (unsigned long long)evals);
+      atomicAdd(p.stats + 1, (unsigned long long)expans);
+      atomicAdd(p.stats + 2, (unsigned long long)adjr);
+    }
+  }
+}
+
+template <class Op, int QC>
+static cudaError_t launch_team_for_op(const SearchParams& p, int grid, size_t smem, cudaStream_t st, bool query_only,
+                                      int* blocks_per_sm) {
+  const int ch = p.g.d4 / 8;
+#define HB_LAUNCH_TEAM(CHV)                                                                                  \
+  do {                                                                                                       \
+    auto kern = search_team_kernel<Op, CHV, QC>;                                                             \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (e != cudaSuccess) return e;                                                                          \
+    if (blocks_per_sm) {                                                                                     \
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, TEAM_THREADS, smem);            \
+      if (e != cudaSuccess) return e;                                                                        \
+    }                                                                                                        \
+    if (!query_only) kern<<<grid, TEAM_THREADS, smem, st>>>(p);                                              \
+    return cudaGetLastError();                                                                               \
+  } while (0)
+  if (ch == 1) HB_LAUNCH_TEAM(1);
+  if (ch == 2) HB_LAUNCH_TEAM(2);
+  if (ch == 4) HB_LAUNCH_TEAM(4);
+#undef HB_LAUNCH_TEAM
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_search_team(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
+                               bool query_only, int* blocks_per_sm) {
+  return dispatch_op(metric, dtype, [&](auto tag) -> cudaError_t {
+    using Op = typename decltype(tag)::type;
+    if constexpr (TeamOp<Op>::value) {
+      if (p.q_smem == 64) return launch_team_for_op<Op, 64>(p, grid, smem, st, query_only, blocks_per_sm);
+      if (p.q_smem == 128) return launch_team_for_op<Op, 128>(p, grid, smem, st, query_only, blocks_per_sm);
+    }
+    return cudaErrorInvalidValue;
+  });
+}
+
+}  // namespace hb

@@ -83,6 +83,13 @@ __device__ __forceinline__ uint32_t ld_keep(const uint32_t* p, uint64_t pol) {
   asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ uint4 ld_keep4(const uint4* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ void st_keep(uint32_t* p, uint32_t v, uint64_t pol) {
   asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }

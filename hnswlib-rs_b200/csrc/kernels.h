@@ -14,7 +14,7 @@ inline int dtype_size(int dt) { return dt == DT_U8 ? 1 : dt == DT_U16 ? 2 : 4; }
 constexpr int SEARCH_THREADS = 256;  // 8 warps = 8 queries in flight per CTA
 constexpr int BUILD_THREADS = 128;   // 4 warps = 4 inserts in flight per CTA
 constexpr int TEAM_THREADS = 32;     // team kernel (search_team.cu): one warp per CTA = 4 queries of 8 lanes each
-constexpr int TEAM_MIN_BLOCKS = 16;  // 16 warps x 4 teams = 64 queries resident per SM, <= 128 registers per thread
+constexpr int TEAM_MIN_BLOCKS = 16;  // 16 warps x 4 teams = 64 queries resident per SM (9 472 per B200), <= 128 registers per thread
 
 // One answer slot.  Same 16-byte layout as the reference's #[repr(C)] Neighbour_api {id: usize, d: f32}
 // (/root/reference/src/libext.rs:64-71); the internal id rides in what is tail padding there.
@@ -71,10 +71,7 @@ inline size_t search_smem_per_warp(int d4, int q_smem) {
 // rows of 128 / 256 / 512 bytes (compile-time chunk count), ef <= 128, no filter
 inline int team_queue_slots(int ef) { return ef <= 64 ? 64 : (ef <= 128 ? 128 : 0); }
 inline bool team_eligible(int d4, int ef) { return (d4 == 8 || d4 == 16 || d4 == 32) && team_queue_slots(ef) != 0; }
-inline size_t team_smem_per_team(int d4, int qc) {
-  const size_t ub = (size_t)d4 * 16 > (size_t)qc * 8 ? (size_t)d4 * 16 : (size_t)qc * 8;
-  return ub + 128;
-}
+inline size_t team_smem_per_team(int d4, int qc) { return (size_t)qc * 8 + 128 + (size_t)d4 * 16; }
 
 struct InsertParams {
   GraphView g;

@@ -64,7 +64,7 @@ Index::Index(int M_, size_t max_elements_, int max_layer_, int ef_c_, int metric
   }
   own_stream_ = stream_;
   sm_count_ = prop.multiProcessorCount;
-  if (const char* k = getenv("HNSW_B200_KERNEL")) kernel_pref_ = strcmp(k, "warp") == 0 ? 1 : 0;
+  if (const char* k = getenv("HNSW_B200_KERNEL")) kernel_pref_ = strcmp(k, "warp") == 0 ? 1 : (strcmp(k, "team") == 0 ? 2 : 0);
   if (const char* k = getenv("HNSW_B200_TVIS_SHIFT")) tvis_scale_shift_ = atoi(k);
   if ((e = cudaMalloc(&d_counter_, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&d_status_, sizeof(int))) != cudaSuccess ||
       (e = cudaMalloc(&d_stats_, 4 * sizeof(unsigned long long))) != cudaSuccess) {
@@ -531,13 +531,17 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
   p.status = d_status_;
   const bool filtered = d_filter_bits != nullptr;
   // kernel choice: the team kernel (8 lanes per query, search_team.cu) whenever it applies, else one warp per query
-  const bool team = !filtered && kernel_pref_ != 1 && entry != INVALID_ID && team_op_supported(metric, dtype) &&
-                    team_eligible(p.g.d4, p.ef);
-  p.q_kind = (filtered || team) ? 0 : queue_kind(p.ef, metric, dtype);
-  p.q_smem = team ? team_queue_slots(p.ef) : queue_slots(p.q_kind, p.ef);
-  size_t spw = team ? 4 * team_smem_per_team(p.g.d4, p.q_smem) : search_smem_per_warp(p.g.d4, p.q_smem);
+  // kernel choice: lean (one warp per query, search_lean.cu) whenever it applies, else the generic warp kernel;
+  // the team kernel (8 lanes per query, search_team.cu) on request (HNSW_B200_KERNEL=team)
+  const bool fast_ok = !filtered && entry != INVALID_ID && team_op_supported(metric, dtype) && team_eligible(p.g.d4, p.ef);
+  const bool team = fast_ok && kernel_pref_ == 2;
+  const bool lean = fast_ok && kernel_pref_ == 0;
+  p.q_kind = (filtered || team || lean) ? 0 : queue_kind(p.ef, metric, dtype);
+  p.q_smem = (team || lean) ? team_queue_slots(p.ef) : queue_slots(p.q_kind, p.ef);
+  size_t spw = team ? 4 * team_smem_per_team(p.g.d4, p.q_smem)
+                    : (lean ? lean_smem_per_warp(p.q_smem) : search_smem_per_warp(p.g.d4, p.q_smem));
   p.smem_per_warp = (int)spw;
-  const int wpb = (team ? TEAM_THREADS : SEARCH_THREADS) / 32;
+  const int wpb = (team ? TEAM_THREADS : (lean ? LEAN_THREADS : SEARCH_THREADS)) / 32;
   const int qpw = team ? 4 : 1;  // queries in flight per warp
   const size_t smem = spw * wpb;
   if (smem > 220 * 1024) return fail("ef / dimension too large for the search kernel's shared memory");
@@ -545,12 +549,13 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
   p.ccap = 0;
   int bps = 0;
   {
-    const auto key = std::make_tuple(team ? 2 : (int)filtered, team ? p.q_smem : p.q_kind, p.g.d4, smem);
+    const auto key = std::make_tuple(team ? 2 : (lean ? 3 : (int)filtered), (team || lean) ? p.q_smem : p.q_kind, p.g.d4, smem);
     auto it = occ_cache_.find(key);
     if (it != occ_cache_.end()) {
       bps = it->second;
     } else {
       if (team) HB_CUDA(launch_search_team(p, metric, dtype, 0, smem, stream_, true, &bps));
+      else if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, 0, smem, stream_, true, &bps));
       else if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, 0, smem, stream_, true, &bps));
       else HB_CUDA(launch_search(p, metric, dtype, 0, smem, stream_, true, &bps));
       occ_cache_[key] = bps;
@@ -585,6 +590,7 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
     HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
     HB_CUDA(cudaEventRecord(ev0_, stream_));
     if (team) HB_CUDA(launch_search_team(p, metric, dtype, grid, smem, stream_, false, nullptr));
+    else if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, grid, smem, stream_, false, nullptr));
     else if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, grid, smem, stream_, false, nullptr));
     else HB_CUDA(launch_search(p, metric, dtype, grid, smem, stream_, false, nullptr));
     HB_CUDA(cudaEventRecord(ev1_, stream_));

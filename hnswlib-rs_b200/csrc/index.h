@@ -155,7 +155,7 @@ class Index {
 
   // visited tables: vis_ serves the warp-per-query kernels, tvis_ the team kernel
   VisitedPool vis_, tvis_;
-  int kernel_pref_ = 0;        // 0 = automatic, 1 = never use the team kernel (env HNSW_B200_KERNEL=warp; A/B measurements)
+  int kernel_pref_ = 0;        // env HNSW_B200_KERNEL (A/B measurements): 0 = automatic (lean), 1 = "warp" (generic kernel), 2 = "team"
   int tvis_scale_shift_ = 0;   // env HNSW_B200_TVIS_SHIFT: scale the team kernel's visited tables by 2^shift (measurements)
 
   // small device scratch

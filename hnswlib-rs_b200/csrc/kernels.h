@@ -13,6 +13,8 @@ inline int dtype_size(int dt) { return dt == DT_U8 ? 1 : dt == DT_U16 ? 2 : 4; }
 
 constexpr int SEARCH_THREADS = 256;  // 8 warps = 8 queries in flight per CTA
 constexpr int BUILD_THREADS = 128;   // 4 warps = 4 inserts in flight per CTA
+constexpr int LEAN_THREADS = 128;     // lean kernel (search_lean.cu): 4 warps = 4 queries in flight per CTA
+constexpr int LEAN_MIN_BLOCKS = 8;    // 32 warps per SM, <= 64 registers per thread
 constexpr int TEAM_THREADS = 32;     // team kernel (search_team.cu): one warp per CTA = 4 queries of 8 lanes each
 constexpr int TEAM_MIN_BLOCKS = 16;  // 16 warps x 4 teams = 64 queries resident per SM (9 472 per B200), <= 128 registers per thread
 
@@ -71,6 +73,7 @@ inline size_t search_smem_per_warp(int d4, int q_smem) {
 // rows of 128 / 256 / 512 bytes (compile-time chunk count), ef <= 128, no filter
 inline int team_queue_slots(int ef) { return ef <= 64 ? 64 : (ef <= 128 ? 128 : 0); }
 inline bool team_eligible(int d4, int ef) { return (d4 == 8 || d4 == 16 || d4 == 32) && team_queue_slots(ef) != 0; }
+inline size_t lean_smem_per_warp(int qc) { return (size_t)qc * 8 + 256; }
 inline size_t team_smem_per_team(int d4, int qc) { return (size_t)qc * 8 + 128 + (size_t)d4 * 16; }
 
 struct InsertParams {
@@ -104,6 +107,8 @@ cudaError_t launch_search_filtered(const SearchParams& p, int metric, int dtype,
                                    bool query_only, int* blocks_per_sm);
 cudaError_t launch_search(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st, bool query_only,
                           int* blocks_per_sm);
+cudaError_t launch_search_lean(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
+                               bool query_only, int* blocks_per_sm);
 cudaError_t launch_search_team(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
                                bool query_only, int* blocks_per_sm);
 

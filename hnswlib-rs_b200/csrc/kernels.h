@@ -14,7 +14,10 @@ inline int dtype_size(int dt) { return dt == DT_U8 ? 1 : dt == DT_U16 ? 2 : 4; }
 constexpr int SEARCH_THREADS = 256;  // 8 warps = 8 queries in flight per CTA
 constexpr int BUILD_THREADS = 128;   // 4 warps = 4 inserts in flight per CTA
 constexpr int LEAN_THREADS = 128;     // lean kernel (search_lean.cu): 4 warps = 4 queries in flight per CTA
-constexpr int LEAN_MIN_BLOCKS = 8;    // 32 warps per SM, <= 64 registers per thread
+#ifndef HB_LEAN_BLOCKS
+#define HB_LEAN_BLOCKS 7
+#endif
+constexpr int LEAN_MIN_BLOCKS = HB_LEAN_BLOCKS;  // 7 CTAs x 4 warps = 28 warps per SM, <= 72 registers per thread (measured: 6, 7, 8 CTAs within 3 %)
 constexpr int TEAM_THREADS = 32;     // team kernel (search_team.cu): one warp per CTA = 4 queries of 8 lanes each
 constexpr int TEAM_MIN_BLOCKS = 16;  // 16 warps x 4 teams = 64 queries resident per SM (9 472 per B200), <= 128 registers per thread
 

@@ -18,6 +18,8 @@
 //     (issuing one bulk copy per row costs ~8 instructions per row: the copy engine takes uniform operands);
 //   * two rows per lane group are reduced with one transposed reduction (3 shuffles for 2 rows, same sums);
 //   * the traversal counters are a template parameter: the production instantiation does not carry them.
+#include <type_traits>
+
 #include "kernels.h"
 #include "team_common.cuh"
 
@@ -82,19 +84,19 @@ __device__ __forceinline__ void lean_merge(uint32_t wa, int lane, uint64_t key, 
     cur[c] = lds64(wa + 8 * (32 * c + lane));
     lb[c] = 0;
   }
-  int rk = 0, ub = 0;
+  int np = 0;  // an accepted key lands at (old entries below it) + (accepted keys below it)
   for (unsigned rem = accmask; rem; rem &= rem - 1) {
     const int j = __ffs(rem) - 1;
     const uint64_t kj = __shfl_sync(FULL, key, j);
-    int below = 0;
+    int below = (accepted && key < kj) ? 1 : 0;  // keys are distinct: ids are (the visited set admits an id once)
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      const bool lt = cur[c] < kj;  // keys are distinct: ids are (the visited set admits an id once)
-      below += __popc(__ballot_sync(FULL, lt));
+      const bool lt = cur[c] < kj;
+      below += lt ? 1 : 0;
       lb[c] += lt ? 0 : 1;
     }
-    rk += (kj < key) ? 1 : 0;
-    if (lane == j) ub = below;
+    below = __reduce_add_sync(FULL, below);
+    if (lane == j) np = below;
   }
   __syncwarp();  // every lane holds its old entries: the slots may be rewritten
   uint32_t bits[NCH];
@@ -112,7 +114,6 @@ __device__ __forceinline__ void lean_merge(uint32_t wa, int lane, uint64_t key, 
       }
     }
   }
-  const int np = rk + ub;
   if (accepted && np < cap) {
     sts64(wa + 8 * np, key);
 #pragma unroll
@@ -128,12 +129,19 @@ __device__ __forceinline__ void lean_merge(uint32_t wa, int lane, uint64_t key, 
   thr = lds64(wa + 8 * (cap - 1));
 }
 
-// Visited::test_and_set with the first probe optionally done ahead of time (`pre`: slot pre_h was read as pre_cv after
-// the last store to the table)
-__device__ __forceinline__ bool lean_test_and_set(Visited& vis, uint32_t id, bool valid, bool pre, uint32_t pre_h, uint32_t pre_cv) {
-  const uint32_t want = vis.tag | id;
+// The visited set of common.cuh (Visited) with its state cut down to what changes: table pointer, epoch, insert count;
+// capacity, hash shift and the epoch/id split are read from the kernel parameters (constant bank) where they are used.
+// test_and_set: the first probe may have been done ahead of time (`pre`: slot pre_h was read as pre_cv after the last
+// store to the table).
+struct LeanVisited {
+  uint32_t* tab;
+  uint32_t epoch, used;
+};
+__device__ __forceinline__ bool lean_test_and_set(const VisitedCfg& c, LeanVisited& vis, int lane, uint32_t id, bool valid, bool pre,
+                                                  uint32_t pre_h, uint32_t pre_cv) {
+  const uint32_t want = (vis.epoch << c.id_bits) | id;
   const uint64_t pol_keep = l2_policy_evict_last();
-  uint32_t h = pre ? pre_h : (id * 2654435761u) >> vis.shift;
+  uint32_t h = pre ? pre_h : (id * 2654435761u) >> c.shift;
   bool pending = valid, fresh = false, first = pre;
   while (__any_sync(FULL, pending)) {
     uint32_t cur = 0;
@@ -143,10 +151,10 @@ __device__ __forceinline__ bool lean_test_and_set(Visited& vis, uint32_t id, boo
     if (pending) {
       if (cur == want) {
         pending = false;  // already visited
-      } else if ((cur >> vis.id_bits) != vis.epoch) {
+      } else if ((cur >> c.id_bits) != vis.epoch) {
         claim = true;  // stale or empty slot
       } else {
-        h = (h + 1) & vis.mask;
+        h = (h + 1) & (c.cap - 1);
       }
     }
     const unsigned claimers = __ballot_sync(FULL, claim);
@@ -154,14 +162,14 @@ __device__ __forceinline__ bool lean_test_and_set(Visited& vis, uint32_t id, boo
       const unsigned same = __match_any_sync(claimers, h);
       const int leader = __ffs(same) - 1;
       const uint32_t lead_id = __shfl_sync(claimers, id, leader);
-      if (lane_id() == leader) {
+      if (lane == leader) {
         st_keep(vis.tab + h, want, pol_keep);
         fresh = true;
         pending = false;
       } else if (lead_id == id) {
         pending = false;  // the same id twice in one chunk: the leader records it
       } else {
-        h = (h + 1) & vis.mask;
+        h = (h + 1) & (c.cap - 1);
       }
     }
     __syncwarp();  // orders this round's stores before the next round's loads
@@ -187,8 +195,10 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_MIN_BLOCKS) search_lean_ker
   const uint64_t pol_rows = l2_policy_evict_first();
 
   const uint32_t slot = blockIdx.x * (LEAN_THREADS / 32) + (threadIdx.x >> 5);
-  Visited vis;
-  vis.init(p.vis, slot);
+  LeanVisited vis;
+  vis.tab = p.vis.tables + (size_t)slot * p.vis.cap;
+  vis.epoch = p.vis.epochs[slot];
+  vis.used = 0;
   unsigned evals = 0, expans = 0, adjr = 0;
   const int cap = p.ef;
 
@@ -270,8 +280,18 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_MIN_BLOCKS) search_lean_ker
     }
 
     // ---- search_layer on the lowest populated layer (hnsw.rs:1531-1542, 940-1057)
-    vis.begin();
-    vis.test_and_set(pivot, lane == 0);  // hnsw.rs:955-956
+    {  // a new search bumps the epoch instead of clearing the table (Visited::begin)
+      const uint32_t epoch_max = (p.vis.id_bits >= 32) ? 0u : ((1u << (32 - p.vis.id_bits)) - 1u);
+      if (vis.epoch >= epoch_max) {
+        for (uint32_t i = lane; i < p.vis.cap; i += 32) vis.tab[i] = 0u;
+        vis.epoch = 0;
+      }
+      vis.epoch += 1;
+      vis.used = 1;
+      __syncwarp();
+      // hnsw.rs:955-956: the table holds nothing of this epoch yet, the entry's home slot is free
+      if (lane == 0) st_keep(vis.tab + ((pivot * 2654435761u) >> p.vis.shift), (vis.epoch << p.vis.id_bits) | pivot, l2_policy_evict_last());
+    }
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < NCH; ++c) sts64(wa + 8 * (32 * c + lane), ~0ull);
@@ -315,7 +335,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_MIN_BLOCKS) search_lean_ker
         if (!use_pre) nid = (b + lane < lcap) ? ids[b + lane] : INVALID_ID;
         const unsigned valid = __ballot_sync(FULL, nid != INVALID_ID);
         if (STATS) adjr += __popc(valid);
-        const bool fresh = lean_test_and_set(vis, nid, nid != INVALID_ID, use_pre, pre_h, pre_cv);  // hnsw.rs:1016-1017
+        const bool fresh = lean_test_and_set(p.vis, vis, lane, nid, nid != INVALID_ID, use_pre, pre_h, pre_cv);  // hnsw.rs:1016-1017
         const unsigned m = __ballot_sync(FULL, fresh);
         const int cnt = __popc(m);
         const bool last = valid != FULL || b + 32 >= lcap;
@@ -325,7 +345,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_MIN_BLOCKS) search_lean_ker
             int pcap;
             const uint32_t* pids = list_ids(G, pre_c, p.layer0, pcap);
             pre_nid = (lane < pcap) ? pids[lane] : INVALID_ID;
-            pre_h = (pre_nid * 2654435761u) >> vis.shift;
+            pre_h = (pre_nid * 2654435761u) >> p.vis.shift;
             pre_cv = 0;
             if (pre_nid != INVALID_ID) pre_cv = ld_keep(vis.tab + pre_h, l2_policy_evict_last());
             pre_ok = true;
@@ -350,7 +370,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_MIN_BLOCKS) search_lean_ker
         }
         if (last) break;  // lists are dense prefixes terminated by INVALID_ID
       }
-      if (vis.overflowing()) {
+      if (vis.used >= p.vis.cap - (p.vis.cap >> 2)) {
         overflow = true;
         break;
       }
@@ -374,7 +394,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_MIN_BLOCKS) search_lean_ker
     if (lane == 0) p.out_count[qi] = count;
     __syncwarp();
   }
-  vis.save(p.vis, slot);
+  if (lane == 0) p.vis.epochs[slot] = vis.epoch;
   if (STATS && p.stats && lane == 0) {
     atomicAdd(p.stats + 0, (unsigned long long)evals);
     atomicAdd(p.stats + 1, (unsigned long long)expans);
@@ -403,8 +423,10 @@ static cudaError_t launch_lean_for_op(const SearchParams& p, int grid, size_t sm
     if (p.stats) HB_LAUNCH_LEAN2(CHV, true); \
     HB_LAUNCH_LEAN2(CHV, false);             \
   } while (0)
+#ifndef HB_FAST_BUILD
   if (ch == 1) HB_LAUNCH_LEAN(1);
   if (ch == 2) HB_LAUNCH_LEAN(2);
+#endif
   if (ch == 4) HB_LAUNCH_LEAN(4);
 #undef HB_LAUNCH_LEAN
 #undef HB_LAUNCH_LEAN2
@@ -415,10 +437,16 @@ cudaError_t launch_search_lean(const SearchParams& p, int metric, int dtype, int
                                bool query_only, int* blocks_per_sm) {
   return dispatch_op(metric, dtype, [&](auto tag) -> cudaError_t {
     using Op = typename decltype(tag)::type;
+#ifdef HB_FAST_BUILD  // scripts/variants.sh: one instantiation, for A/B builds
+    if constexpr (std::is_same<Op, OpL2>::value) {
+      if (p.q_smem == 64) return launch_lean_for_op<Op, 64>(p, grid, smem, st, query_only, blocks_per_sm);
+    }
+#else
     if constexpr (TeamOp<Op>::value) {
       if (p.q_smem == 64) return launch_lean_for_op<Op, 64>(p, grid, smem, st, query_only, blocks_per_sm);
       if (p.q_smem == 128) return launch_lean_for_op<Op, 128>(p, grid, smem, st, query_only, blocks_per_sm);
     }
+#endif
     return cudaErrorInvalidValue;
   });
 }

@@ -2,29 +2,41 @@
 """bench.py — queries/s of HNSW search at matched recall@10 (BASELINE.json metric).
 
 One "step" = one pass of the hot path (greedy descent + ef-bounded layer-0 expansion,
-reference src/hnsw.rs:1487-1580 + 922-1064) over one batch of `--nq` synthetic queries against a
-graph of `--n` points built on the GPU by this engine.
+reference src/hnsw.rs:1487-1580 + 922-1064) over one batch of synthetic queries against a graph built on the GPU by
+this engine.  `--config` picks the workload (BASELINE.json configs[0..4]); the default is c2, the configuration the
+metric is quoted on:
 
-Default workload = BASELINE.json configs[1]: SIFT1M-shape synthetic, 1M x d=128 f32 L2, M=16,
-ef_construction=200, 10k queries, k=10, ef=64, one GPU.
+  c1  random.rs shape: 10 000 x d=25 f32 L2, M=16 ef_c=200, 1 000 queries k=10 ef=24
+  c2  SIFT1M shape: 1 000 000 x d=128 f32 L2, M=16 ef_c=200, 10 000 queries k=10 ef=64   (default)
+  c3  GloVe-25 shape: 1 183 514 x d=25 unit vectors, DistCosine (angular), M=24 ef_c=800, 10 000 queries k=10 ef=128
+  c3dot  same with DistDot on the normalised vectors, what the reference's own example runs "to spare cpu"
+  c4  MNIST-784 shape: 60 000 x d=784 f32 L2, M=32 ef_c=400, 10 000 queries k=10 ef=200
+  c5  c2's graph, 1 000 000 queries per step query-sharded over the GPUs (strong scaling)
 
   value      queries/s, inputs resident in HBM, K launches timed with CUDA events on the launch stream
-  e2e        same metric through the C-ABI call a user makes (hnsw_b200_search_flat) with HOST buffers:
-             H2D of the queries and D2H of the answers inside the timed region
+  e2e        the same metric through the C-ABI call a user makes with HOST buffers, H2D of the queries and D2H of the
+             answers inside the timed region: hnsw_b200_search_flat; at N > 1 ONE call on rank 0's handle after
+             hnsw_b200_replicate, the library sharding the batch over the N GPUs (e2e.per_rank: every rank calling
+             search_flat on its own shard).  e2e.row_pointers (N = 1): the reference's own entry point
+             parallel_search_neighbours_f32 with pageable row pointers and malloc'ed answers
   roofline   algorithmic bytes (E*d*4 + A*4 + d*4 + k*16 per query, E/A counted by the kernel itself and
              equal to the oracle's counters, tests/test_gpu_search.py) / kernel time vs measured HBM peak
   cpu_baseline  the CPU restatement (oracle, MODE_STD + reference-shaped sums) of the same path on the SAME
              graph and queries, all host threads, bounded sample
   --impl reference   the CPU path alone (oracle-built graph with all host threads, then timed searches)
 
-Multi-GPU (torchrun, one process per GPU): rank 0 builds, the frozen index is broadcast over NCCL, every
-rank searches its own shard of nq queries per step (weak scaling), answers are all-gathered over NCCL
-inside the timed region.
+Multi-GPU (torchrun, one process per GPU): rank 0 builds; the library itself opens an NCCL communicator
+(hnsw_b200_nccl_init, the unique id travels over torch.distributed) and broadcasts the frozen index
+(hnsw_b200_nccl_broadcast_index); every rank searches its own shard (no data-path collective); the answers of step i are
+all-gathered (hnsw_b200_nccl_allgather) on a second stream while step i+1 searches.  Every replica answers a shared probe
+batch and is compared with rank 0 before anything is timed.
 """
 import argparse
+import ctypes
 import importlib
 import json
 import os
+import platform
 import subprocess
 import sys
 import threading
@@ -35,25 +47,52 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+PRESETS = {
+    "c1": dict(n=10000, d=25, nq=1000, M=16, efc=200, k=10, ef=24, metric="DistL2", data="uniform",
+               name="C1 random.rs shape"),
+    "c2": dict(n=1000000, d=128, nq=10000, M=16, efc=200, k=10, ef=64, metric="DistL2", data="clustered",
+               name="C2 SIFT1M-shape synthetic"),
+    "c3": dict(n=1183514, d=25, nq=10000, M=24, efc=800, k=10, ef=128, metric="DistCosine", data="unit",
+               name="C3 GloVe-25-shape synthetic (angular)"),
+    "c3dot": dict(n=1183514, d=25, nq=10000, M=24, efc=800, k=10, ef=128, metric="DistDot", data="unit",
+                  name="C3 GloVe-25-shape synthetic (angular as DistDot on unit vectors)"),
+    "c4": dict(n=60000, d=784, nq=10000, M=32, efc=400, k=10, ef=200, metric="DistL2", data="uniform",
+               name="C4 MNIST-784-shape synthetic"),
+    "c5": dict(n=1000000, d=128, nq=1000000, M=16, efc=200, k=10, ef=64, metric="DistL2", data="clustered",
+               name="C5 SIFT1M-shape synthetic, 1M queries query-sharded"),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1000000)
-    ap.add_argument("--d", type=int, default=128)
-    ap.add_argument("--nq", type=int, default=10000)
-    ap.add_argument("--M", type=int, default=16)
-    ap.add_argument("--efc", type=int, default=200)
-    ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--ef", type=int, default=64)
-    ap.add_argument("--metric", default="DistL2")
-    ap.add_argument("--data", default="clustered", choices=["clustered", "uniform", "unit"])
+    ap.add_argument("--config", default="c2", choices=sorted(PRESETS))
+    for name, typ in (("n", int), ("d", int), ("nq", int), ("M", int), ("efc", int), ("k", int), ("ef", int), ("metric", str),
+                      ("data", str)):
+        ap.add_argument("--" + name, type=typ, default=None, help="override the preset")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    preset = PRESETS[a.config]
+    a.custom = False
+    for key, val in preset.items():
+        if key == "name":
+            continue
+        if getattr(a, key) is None:
+            setattr(a, key, val)
+        elif getattr(a, key) != val:
+            a.custom = True
+    a.preset_name = preset["name"]
+    big = a.config == "c5"
+    if a.steps is None:
+        a.steps = 5 if big else 100
+    if a.warmup is None:
+        a.warmup = 3 if big else 10
+    a.strong = big
+    return a
 
 
 class ClockSampler:
@@ -139,13 +178,53 @@ def recall_stats(ids, dists, counts, t_ids, t_d):
     return rid / t_ids.shape[0], rball / t_ids.shape[0]
 
 
-def default_workload(a):
-    return (a.n, a.d, a.nq, a.M, a.efc, a.k, a.ef, a.metric, a.data) == (1000000, 128, 10000, 16, 200, 10, 64, "DistL2", "clustered")
+
+def workload_name(a, world=1):
+    per = a.nq // world if a.strong else a.nq
+    q = (f"{a.nq} queries/step over {world} GPU(s) ({per}/GPU)" if a.strong else f"{a.nq} queries/step/GPU")
+    return (f"{a.preset_name}{' (custom overrides)' if a.custom else ''} ({a.data}): {a.n} x d={a.d} f32 {a.metric}, M={a.M} "
+            f"ef_c={a.efc}, {q} k={a.k} ef={a.ef}")
 
 
-def workload_name(a):
-    return (f"SIFT1M-shape synthetic ({a.data}): {a.n} x d={a.d} f32 {a.metric}, M={a.M} ef_c={a.efc}, "
-            f"{a.nq} queries/step/GPU k={a.k} ef={a.ef}")
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return platform.processor() or "unknown"
+
+
+def committed_traffic(a):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the search kernel on the default workload, read
+    from the ncu --set full summary committed under profiles/ (None for any other workload)."""
+    if a.config != "c2" or a.custom:
+        return None, None
+    path = os.path.join(ROOT, "profiles", "r2_search_lean_kernel_ncu_full_selected.csv")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        tot = 0.0
+        for ln in open(path):
+            f = ln.strip().split(",")
+            if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[2]) * scale[f[1]]
+        return (tot or None), os.path.relpath(path, ROOT)
+    except (OSError, ValueError, KeyError, IndexError):
+        return None, None
+
+
+def best_threads(o, Q, a, cores):
+    """all logical CPUs vs one thread per physical core (hyper-threads share the load units): keep the faster"""
+    best_t, best_q = cores, 0.0
+    for nt in sorted({cores, max(1, cores // 2)}, reverse=True):
+        o.search_batch(Q, a.k, a.ef, nthreads=nt)
+        t0 = time.perf_counter()
+        o.search_batch(Q, a.k, a.ef, nthreads=nt)
+        q = len(Q) / (time.perf_counter() - t0)
+        if q > best_q:
+            best_t, best_q = nt, q
+    return best_t
 
 
 # ------------------------------------------------------------------------------------------- reference arm
@@ -153,7 +232,7 @@ def run_reference(a, rank, world):
     """The reference's own CPU implementation of the path.  The Rust crate cannot be built on this box
     (no cargo/rustc), so this times the CPU restatement (oracle/, kind "port") in its literal mode:
     racy parallel insert with every host thread (hnsw.rs:1224-1238), then parallel_search
-    (hnsw.rs:1612-1635) of the same query batch, MODE_STD heaps + reference-shaped SIMD sums."""
+    (hnsw.rs:1612-1635) of a query batch, MODE_STD heaps + reference-shaped SIMD sums."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -162,41 +241,34 @@ def run_reference(a, rank, world):
     po.build()
     cores = os.cpu_count() or 1
     X = pkg.datagen.make(a.data, a.n, a.d, 1)
-    Q = pkg.datagen.make(a.data, a.nq, a.d, 2)
+    nq = min(a.nq, 10000)   # a bounded sample of the step (c5's step is 1M queries)
+    Q = pkg.datagen.make(a.data, nq, a.d, 2)
     o = po.Oracle(a.M, a.n, 16, a.efc, a.metric, a.d, mode=po.MODE_STD, order=po.ORDER_REF)
     t0 = time.perf_counter()
     o.insert_batch(X, nthreads=cores)
     build_s = time.perf_counter() - t0
-    # all logical CPUs vs one thread per physical core: keep the faster for the timed steps
-    best_t, best_q = cores, 0.0
-    for nt in sorted({cores, max(1, cores // 2)}, reverse=True):
-        o.search_batch(Q, a.k, a.ef, nthreads=nt)
-        t0 = time.perf_counter()
-        o.search_batch(Q, a.k, a.ef, nthreads=nt)
-        q = a.nq / (time.perf_counter() - t0)
-        if q > best_q:
-            best_t, best_q = nt, q
-    threads = best_t
+    threads = best_threads(o, Q, a, cores)
     for _ in range(a.warmup):
         o.search_batch(Q, a.k, a.ef, nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(a.steps):
         res = o.search_batch(Q, a.k, a.ef, nthreads=threads)
     dt = time.perf_counter() - t0
-    qps = a.steps * a.nq / dt
-    nt = min(1000, a.nq)
+    qps = a.steps * nq / dt
+    nt = min(1000, nq)
     ti, td = po.bruteforce(X, Q[:nt], a.k, a.metric)
     # origin ids == row numbers of X; internal ids are NOT (a racy parallel insert numbers points in arrival order)
     rid, rball = recall_stats(res[0][:nt], res[1][:nt], res[4][:nt], ti, td)
     line = {
         "impl": "reference", "metric": "queries/sec @ recall@10", "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "recall_at_10": rid, "recall_at_10_ball": rball,
+        "scaling": "strong" if a.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a, a.gpus), "recall_at_10": rid, "recall_at_10_ball": rball,
                    "graph": "built by the CPU restatement (parallel insert, all host threads)", "build_s": build_s},
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": f"{a.steps} x {a.nq} queries, full batch each step, {threads} threads "
-                                   f"(best of all logical CPUs / half); graph built with {cores} threads"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "threads": threads, "kind": "port",
+                         "cpu_model": cpu_model(), "logical_cpus": cores, "numa_interleave": "first touch by the build threads",
+                         "sample": f"{a.steps} x {nq} queries per step, {threads} threads (best of all logical CPUs / half); "
+                                   f"graph built with {cores} threads"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -204,61 +276,95 @@ def run_reference(a, rank, world):
 
 
 # ------------------------------------------------------------------------------------------- our arm
+def shard_bounds(n, rank, world):
+    """contiguous shard [lo, hi) of n items for `rank` (sizes differ by at most one)"""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 def run_ours(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     pkg = importlib.import_module("hnswlib-rs_b200")
-    replicate = importlib.import_module("hnswlib-rs_b200.replicate")
     dev = local_rank
     torch.cuda.set_device(dev)
     multi = world > 1
     t_setup = time.perf_counter()
+    lo, hi = shard_bounds(a.nq, rank, world) if a.strong else (0, a.nq)
+    nq = hi - lo                                   # this rank's queries per step
+    total_per_step = a.nq if a.strong else a.nq * world
 
-    # ---- graph: rank 0 builds on its GPU; replicas receive the frozen arrays over NCCL
+    # ---- graph: rank 0 builds on its GPU; the library broadcasts the frozen index over its own NCCL communicator
     h = pkg.Hnsw(a.M, a.n, 16, a.efc, a.metric, device=dev)
-    build_s = 0.0
-    X = None
+    build_s = bcast_s = 0.0
     if rank == 0:
         X = pkg.datagen.make(a.data, a.n, a.d, 1)
         t0 = time.perf_counter()
         h.insert_flat(X)
         build_s = time.perf_counter() - t0
-    bcast_s = 0.0
+        del X
     if multi:
+        uid = torch.from_numpy(pkg.Hnsw.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
+        dist.broadcast(uid, 0)                     # 128 bytes of ncclUniqueId, by the host's own means
         t0 = time.perf_counter()
-        replicate.broadcast_index(h, 0, f"cuda:{dev}")      # ncclBroadcast of the frozen arrays
+        h.nccl_init(world, rank, uid.cpu().numpy())
+        h.nccl_broadcast_index(0)                  # ncclBroadcast of header + 9 device arrays, inside the library
         bcast_s = time.perf_counter() - t0
+        # every replica answers a shared probe batch; the answers must equal rank 0's
+        probe = pkg.datagen.make(a.data, 512, a.d, 4242)
+        ids = torch.from_numpy(h.search_flat(probe, a.k, a.ef, with_pid=False)[2].astype(np.int64)).cuda()
+        ref = ids.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([int(torch.equal(ids, ref))], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if int(same.item()) != 1:
+            raise RuntimeError("a replica's answers differ from rank 0's")
 
     # ---- queries: NB rotating batches per rank, seeded per rank; pinned host copies + device copies
-    NB = 4
-    q_host = [torch.from_numpy(pkg.datagen.make(a.data, a.nq, a.d, 2 + 1000 * rank + b)).pin_memory() for b in range(NB)]
+    NB = 4 if nq <= 20000 else 1
+    q_host = [torch.from_numpy(pkg.datagen.make(a.data, nq, a.d, 2 + 1000 * rank + b)).pin_memory() for b in range(NB)]
     q_dev = [q.cuda(non_blocking=True) for q in q_host]
-    out_dev = torch.empty((a.nq, a.k, 16), dtype=torch.uint8, device="cuda")        # Neighbour_api[nq][k]
-    cnt_dev = torch.empty((a.nq,), dtype=torch.int32, device="cuda")
-    gather_dev = torch.empty((world * a.nq, a.k, 16), dtype=torch.uint8, device="cuda") if multi else None
+    out_dev = [torch.empty((nq, a.k, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]   # Neighbour_api[nq][k]
+    cnt_dev = torch.empty((nq,), dtype=torch.int32, device="cuda")
+    same_shards = (not a.strong) or a.nq % world == 0
+    gather_dev = [torch.empty((world * nq, a.k, 16), dtype=torch.uint8, device="cuda") for _ in range(2)] if multi and same_shards else None
     torch.cuda.synchronize()
-    # a dedicated (non-default) torch stream: the library's kernels, torch's events and the NCCL collectives all
-    # go through it, so torch.cuda.Event brackets exactly the launches of the timed region
+    # a dedicated (non-default) torch stream: the library's kernels and torch's events go through it, so
+    # torch.cuda.Event brackets exactly the launches of the timed region; the all-gathers run on a second stream
     stream = torch.cuda.Stream(device=dev)
+    gstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_gath = [torch.cuda.Event() for _ in range(2)]
 
-    def step_device(b, sync=False):
-        ms = h.search_device(q_dev[b % NB].data_ptr(), a.nq, a.k, a.ef, out_dev.data_ptr(), cnt_dev.data_ptr(), sync=sync)
-        if multi:
-            dist.all_gather_into_tensor(gather_dev, out_dev)   # ncclAllGather of the answers
+    def step_device(i, sync=False):
+        b = i & 1
+        if gather_dev is not None and i >= 2:
+            stream.wait_event(ev_gath[b])          # the all-gather that read out_dev[b] two steps ago has finished
+        ms = h.search_device(q_dev[i % NB].data_ptr(), nq, a.k, a.ef, out_dev[b].data_ptr(), cnt_dev.data_ptr(), sync=sync)
+        if gather_dev is not None:                 # ncclAllGather of step i's answers, overlapped with step i+1's search
+            ev_done[b].record(stream)
+            gstream.wait_event(ev_done[b])
+            h.nccl_allgather(out_dev[b].data_ptr(), gather_dev[b].data_ptr(), nq * a.k * 16, gstream.cuda_stream)
+            ev_gath[b].record(gstream)
         return ms
+
+    def drain():
+        if gather_dev is not None:
+            stream.wait_stream(gstream)
 
     # ---- one instrumented pass: traversal counters (algorithmic bytes) and recall vs exact brute force
     h.enable_stats(True)
     step_device(0, sync=True)
     st = h.get_stats()
     h.enable_stats(False)
-    E, A = st["evals"] / a.nq, st["adj_read"] / a.nq
+    E, A = st["evals"] / nq, st["adj_read"] / nq
     bytes_per_query = E * a.d * 4 + A * 4 + a.d * 4 + a.k * 16
     rid = rball = None
     if rank == 0:
-        nt = min(1000, a.nq)
+        nt = min(1000, nq)
         qn = q_host[0][:nt].numpy()
         ti, td = h.bruteforce(qn, a.k)                      # exact ground truth (K5 kernel)
         o_, d_, i_, _, c_ = h.search_flat(qn, a.k, a.ef)
@@ -272,6 +378,7 @@ def run_ours(a, rank, world, local_rank):
     # ---- device-resident: W warm-up steps, then exactly K steps between CUDA events on the launch stream
     for i in range(a.warmup):
         step_device(i)
+    drain()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(dev) as clk:
@@ -279,6 +386,7 @@ def run_ours(a, rank, world, local_rank):
         e0.record(stream)
         for i in range(a.steps):
             step_device(i)
+        drain()
         e1.record(stream)
         barrier()
     dev_ms = e0.elapsed_time(e1)
@@ -286,15 +394,15 @@ def run_ours(a, rank, world, local_rank):
         raise RuntimeError("visited table overflow during the timed region")
     clocks = clk.summary()
     # per-launch kernel duration (CUDA events inside the library, around the kernel alone)
-    kms = [h.search_device(q_dev[i % NB].data_ptr(), a.nq, a.k, a.ef, out_dev.data_ptr(), cnt_dev.data_ptr(), sync=True)
+    kms = [h.search_device(q_dev[i % NB].data_ptr(), nq, a.k, a.ef, out_dev[0].data_ptr(), cnt_dev.data_ptr(), sync=True)
            for i in range(min(a.steps, 10))]
     kernel_ms = float(np.mean(kms))
 
-    # ---- steady-state reference point (not the metric): one launch of 10x the step's queries, where ramp-up and tail of
-    # the 2-wave step no longer dominate (BASELINE configs[4] runs 125 000 queries per GPU, i.e. in this regime)
+    # ---- steady-state reference point (not the metric): one launch of 10x the step's queries, where ramp-up and tail
+    # of the 2-wave step no longer dominate (BASELINE configs[4] runs 125 000 queries per GPU, i.e. in this regime)
     steady = None
-    if rank == 0 and not multi:
-        nbig = 10 * a.nq
+    if rank == 0 and not multi and nq <= 20000:
+        nbig = 10 * nq
         qb = torch.from_numpy(pkg.datagen.make(a.data, nbig, a.d, 777)).cuda()
         ob = torch.empty((nbig, a.k, 16), dtype=torch.uint8, device="cuda")
         cb = torch.empty((nbig,), dtype=torch.int32, device="cuda")
@@ -304,74 +412,102 @@ def run_ours(a, rank, world, local_rank):
                   "algorithmic_GBps": bytes_per_query * nbig / ms_big / 1e6}
         del qb, ob, cb
 
-    # ---- end to end through the C-ABI call with host buffers (H2D + kernel + D2H per step)
-    gloo = dist.new_group(backend="gloo") if multi else None
-    qh_np = [q.numpy() for q in q_host]
+    # ---- end to end through the C-ABI calls with host buffers (H2D + kernel + D2H per step)
     h.set_stream(None)
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
+    qh_np = [q.numpy() for q in q_host]
 
-    def step_e2e(b):
-        res = h.search_flat(qh_np[b % NB], a.k, a.ef, with_internal=False, with_pid=False)   # ids + distances + counts
-        if multi:   # answers to rank 0 (host side, gloo)
-            t = torch.from_numpy(res[0].view(np.int64))   # gloo has no uint64
-            gl = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-            dist.gather(t, gl, dst=0, group=gloo)
-        return res
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fn(i)
+        barrier()
+        return time.perf_counter() - t0
 
-    for i in range(a.warmup):
-        step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(a.steps):
-        step_e2e(i)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    # (1) every rank calls hnsw_b200_search_flat on its own shard (ids + distances + counts back in host memory)
+    per_rank_s = timed(lambda i: h.search_flat(qh_np[i % NB], a.k, a.ef, with_internal=False, with_pid=False), a.steps, a.warmup)
+    # (2) N > 1: ONE call on rank 0's handle, the library shards the batch over all the box's GPUs
+    one_call_s = None
+    if multi:
+        big = None
+        if rank == 0:
+            h.replicate(list(range(world)))       # copies on the other GPUs, NCCL inside this process
+            big = [torch.from_numpy(pkg.datagen.make(a.data, total_per_step, a.d, 9000 + b)).pin_memory().numpy()
+                   for b in range(2 if total_per_step <= 200000 else 1)]
+        one_call_s = timed(lambda i: h.search_flat(big[i % len(big)], a.k, a.ef, with_internal=False, with_pid=False)
+                           if rank == 0 else None, a.steps, a.warmup)
+        if rank == 0:
+            h.replicate([dev])
+    # (3) N = 1: the reference's own entry point, pageable row pointers, one malloc'ed Neighbourhood per query
+    rowptr_s = None
+    if not multi and nq <= 100000:
+        rows = [np.array(r) for r in qh_np[0]]    # pageable copies, one allocation per query
+        L, suf = h._L, h._suf
+        ptrs = (ctypes.c_void_p * nq)(*[r.ctypes.data for r in rows])
+        fn = getattr(L, "parallel_search_neighbours_" + suf)
+
+        def call(_i):
+            res = fn(h._h, nq, a.d, ptrs, a.k, a.ef)
+            if not res:
+                raise RuntimeError(pkg.last_error())
+            L.hnsw_b200_free_vec_api(res)
+        rowptr_s = timed(call, a.steps, min(a.warmup, 3))
 
     # ---- max over ranks
+    times = [dev_ms, per_rank_s * 1e3, kernel_ms, (one_call_s or 0.0) * 1e3]
     if multi:
-        t = torch.tensor([dev_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor(times, dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, kernel_ms = t.tolist()
-        e2e_s = e2e_ms / 1e3
-    total_q = a.steps * a.nq * world
+        times = t.tolist()
+    dev_ms, per_rank_ms, kernel_ms, one_call_ms = times
+    total_q = a.steps * total_per_step
     value = total_q / (dev_ms / 1e3)
-    e2e_v = total_q / e2e_s
+    e2e_per_rank = total_q / (per_rank_ms / 1e3)
+    e2e_v = total_q / (one_call_ms / 1e3) if multi else e2e_per_rank
 
     if rank != 0:
         return
     peak, peak_src = measured_peak_gbs()
-    achieved = bytes_per_query * a.nq / (kernel_ms / 1e3) / 1e9
+    achieved = bytes_per_query * nq / (kernel_ms / 1e3) / 1e9
+    traffic, traffic_src = committed_traffic(a)
+    e2e = {"value": e2e_v, "unit": "queries/s", "h2d_bytes_per_step": total_per_step * a.d * 4,
+           "d2h_bytes_per_step": total_per_step * a.k * 16 + total_per_step * 4,
+           "call": ("one hnsw_b200_search_flat call on rank 0's handle after hnsw_b200_replicate: the library shards the "
+                    f"batch of {total_per_step} queries over {world} GPUs" if multi else "hnsw_b200_search_flat, pinned host buffers"),
+           "per_rank": {"value": e2e_per_rank, "unit": "queries/s",
+                        "call": "every rank: hnsw_b200_search_flat on its own shard, pinned host buffers"}}
+    if rowptr_s is not None:
+        e2e["row_pointers"] = {"value": a.steps * nq / rowptr_s, "unit": "queries/s",
+                               "call": f"parallel_search_neighbours_f32: {nq} pageable row pointers in, malloc'ed "
+                                       "Vec_api<Neighbourhood_api> out and freed, per step"}
     line = {
         "metric": "queries/sec @ recall@10", "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
+        "scaling": "strong" if a.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": workload_name(a), "recall_at_10": rid, "recall_at_10_ball": rball,
+            "workload": workload_name(a, world), "preset": a.config, "recall_at_10": rid, "recall_at_10_ball": rball,
             "graph": "built on the GPU by this engine (batched insert)", "build_s": build_s,
             "index_broadcast_s": bcast_s, "evals_per_query": E, "adj_ids_per_query": A,
-            "l2": f"no flush: working set (point store + adjacency {a.n * (a.d * 4 + a.M * 8) / 1e6:.0f} MB) exceeds the 126 MB L2; "
-                  f"{NB} query batches rotated",
-            "parallelism": f"query-sharded x{world}, index replicated (ncclBroadcast), answers ncclAllGather" if multi else "1 GPU",
+            "l2": f"no flush: working set (point store + adjacency {a.n * (a.d * 4 + a.M * 8) / 1e6:.0f} MB) "
+                  f"{'exceeds' if a.n * (a.d * 4 + a.M * 8) > 126e6 else 'FITS IN'} the 126 MB L2; {NB} query batch(es) rotated",
+            "parallelism": (f"query-sharded x{world}, index replicated (ncclBroadcast inside the library), answers ncclAllGather "
+                            "on a second stream, overlapped with the next step; replicas checked against rank 0") if multi else "1 GPU",
         },
-        "clocks": clocks,
-        "e2e": {"value": e2e_v, "unit": "queries/s", "h2d_bytes_per_step": a.nq * a.d * 4,
-                "d2h_bytes_per_step": a.nq * a.k * 16 + a.nq * 4},
-        "gpu_launches": a.steps,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": TRAFFIC_BYTES_PER_LAUNCH if default_workload(a) else None, "peak_source": peak_src, "kernel": "search_kernel",
-                     "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per_query * a.nq},
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "search_lean_kernel",
+                     "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per_query * nq},
     }
     if steady:
         steady["frac_of_peak"] = steady["algorithmic_GBps"] / peak
         line["config"]["steady_state"] = steady
     if world == 1 and not a.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(a, h, qh_np[0])
+        line["cpu_baseline"] = cpu_baseline(a, h, qh_np[0][:10000])
     line["config"]["setup_s"] = time.perf_counter() - t_setup
     emit(line)
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum of one search_kernel launch on the DEFAULT workload, from the
-# ncu --set full capture summarised in profiles/ (reported only when the run uses the default workload)
-TRAFFIC_BYTES_PER_LAUNCH = 6.407e9   # profiles/r1_final_search_kernel_ncu_full_selected.csv: 6.078 GB read + 0.329 GB written
 
 
 def cpu_baseline(a, h, Q):
@@ -380,7 +516,7 @@ def cpu_baseline(a, h, Q):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle as po
     po.build()
-    cores = os.cpu_count() or 1
+    logical = os.cpu_count() or 1
     lv, rk, og, entry = h.export_points()
     # the graph is imported by ONE thread: interleave its pages over the NUMA nodes, as the reference's own
     # multi-threaded build would spread them by first touch (otherwise every search thread hammers one node)
@@ -389,26 +525,18 @@ def cpu_baseline(a, h, Q):
     maxl = int(lv.max()) + 1 if len(lv) else 1
     o.import_graph(h.export_vectors(), og, lv, entry, {l: h.export_layer(l) for l in range(min(16, maxl + 1))})
     po.numa_interleave(False)
-    # all logical CPUs vs one thread per physical core (hyper-threads share the load units): keep the faster
-    best_t, best_q = cores, 0.0
-    for nt in sorted({cores, max(1, cores // 2)}, reverse=True):
-        o.search_batch(Q, a.k, a.ef, nthreads=nt)
-        t0 = time.perf_counter()
-        o.search_batch(Q, a.k, a.ef, nthreads=nt)
-        q = a.nq / (time.perf_counter() - t0)
-        if q > best_q:
-            best_t, best_q = nt, q
-    cores = best_t
+    threads = best_threads(o, Q, a, logical)
     reps, t0 = 0, time.perf_counter()
     while True:
-        o.search_batch(Q, a.k, a.ef, nthreads=cores)
+        o.search_batch(Q, a.k, a.ef, nthreads=threads)
         reps += 1
         dt = time.perf_counter() - t0
         if dt >= a.cpu_seconds or reps >= 2000:
             break
-    return {"value": reps * a.nq / dt, "unit": "queries/s", "cores": cores, "kind": "port",
-            "sample": f"{reps} passes over the same {a.nq}-query batch on the GPU-built graph ({dt:.1f} s wall), "
-                      f"{cores} threads (best of all logical CPUs / half), numa_interleave={'on' if numa == 0 else 'refused'}"}
+    return {"value": reps * len(Q) / dt, "unit": "queries/s", "cores": threads, "threads": threads, "kind": "port",
+            "cpu_model": cpu_model(), "logical_cpus": logical, "numa_interleave": "on" if numa == 0 else "refused",
+            "sample": f"{reps} passes over the same {len(Q)}-query batch on the GPU-built graph ({dt:.1f} s wall), "
+                      f"{threads} threads (best of all logical CPUs / half)"}
 
 
 class _OnlyJsonOnStdout:

@@ -127,6 +127,9 @@ static const Neighbourhood_api* search_any(const void* hv, size_t len, const voi
   return out;
 }
 
+// a batch is split over the replicas when there are any and every device gets a worthwhile share
+static bool use_shards(const Index* ix, size_t nq) { return ix->replica_count() > 0 && nq >= 64 * (ix->replica_count() + 1); }
+
 struct VecApiBox {
   Vec_api_Neighbourhood_api v;  // first member: the pointer handed to the caller
   Neighbourhood_api* hoods;
@@ -145,8 +148,17 @@ static const Vec_api_Neighbourhood_api* parallel_search_any(const void* hv, size
   box->hoods = (Neighbourhood_api*)malloc(sizeof(Neighbourhood_api) * (nb_vec ? nb_vec : 1));
   box->block = (Neighbour_api*)malloc(sizeof(Neighbour_api) * (nb_vec ? nb_vec * knbn : 1));
   std::vector<int32_t> cnt(nb_vec);
-  if (pass(h->ix, h->ix->search_host(nullptr, data, nb_vec, (int)vec_len, knbn, ef_search, nullptr,
-                                     (NeighbourOut*)box->block, cnt.data()))) {
+  int rc;
+  if (use_shards(h->ix, nb_vec)) {  // replicas on other GPUs: every device answers its slice of the batch in place
+    NeighbourOut* block = (NeighbourOut*)box->block;
+    int32_t* cp = cnt.data();
+    rc = h->ix->for_each_shard(nb_vec, [=](Index* rx, size_t first, size_t count) {
+      return rx->search_host(nullptr, data + first, count, (int)vec_len, knbn, ef_search, nullptr, block + first * knbn, cp + first);
+    });
+  } else {
+    rc = h->ix->search_host(nullptr, data, nb_vec, (int)vec_len, knbn, ef_search, nullptr, (NeighbourOut*)box->block, cnt.data());
+  }
+  if (pass(h->ix, rc)) {
     free(box->hoods);
     free(box->block);
     free(box);
@@ -466,24 +478,29 @@ int hnsw_b200_search_flat(const void* h, const void* queries, uint64_t nq, uint6
     if (r) return r;
     fb = bits.data();
   }
-  const NeighbourOut* tmp = nullptr;
-  const int32_t* cnts = nullptr;
-  int r = pass(ix, ix->search_host_staged(queries, nullptr, nq, (int)dim, knbn, ef_search, fb, &tmp, &cnts));
-  if (r) return r;
-  memcpy(out_counts, cnts, nq * sizeof(int32_t));
-  for (uint64_t i = 0; i < nq; ++i)
-    for (uint64_t j = 0; j < knbn; ++j) {
-      const uint64_t o = i * knbn + j;
-      const bool valid = (int64_t)j < out_counts[i];
-      out_ids[o] = valid ? tmp[o].origin : ~0ull;
-      out_dist[o] = valid ? tmp[o].dist : __builtin_inff();
-      if (out_internal) out_internal[o] = valid ? tmp[o].internal : hb::INVALID_ID;
-      if (out_pid) {  // PointId(level, rank), hnsw.rs:46
-        out_pid[2 * o] = valid ? (int32_t)ix->h_level[tmp[o].internal] : -1;
-        out_pid[2 * o + 1] = valid ? ix->h_rank[tmp[o].internal] : -1;
+  // one device, or one contiguous shard per device: search, then unpack the shard's answers into the caller's arrays
+  const size_t qrow = (size_t)dim * ix->es;
+  auto run = [=](Index* rx, size_t first, size_t count) -> int {
+    const NeighbourOut* tmp = nullptr;
+    const int32_t* cnts = nullptr;
+    int r = rx->search_host_staged((const char*)queries + first * qrow, nullptr, count, (int)dim, knbn, ef_search, fb, &tmp, &cnts);
+    if (r) return r;
+    memcpy(out_counts + first, cnts, count * sizeof(int32_t));
+    for (uint64_t i = 0; i < count; ++i)
+      for (uint64_t j = 0; j < knbn; ++j) {
+        const uint64_t s = i * knbn + j, o = (first + i) * knbn + j;
+        const bool valid = (int64_t)j < cnts[i];
+        out_ids[o] = valid ? tmp[s].origin : ~0ull;
+        out_dist[o] = valid ? tmp[s].dist : __builtin_inff();
+        if (out_internal) out_internal[o] = valid ? tmp[s].internal : hb::INVALID_ID;
+        if (out_pid) {  // PointId(level, rank), hnsw.rs:46
+          out_pid[2 * o] = valid ? (int32_t)rx->h_level[tmp[s].internal] : -1;
+          out_pid[2 * o + 1] = valid ? rx->h_rank[tmp[s].internal] : -1;
+        }
       }
-    }
-  return 0;
+    return 0;
+  };
+  return pass(ix, use_shards(ix, nq) ? ix->for_each_shard(nq, run) : run(ix, 0, nq));
 }
 
 int hnsw_b200_search_device(const void* h, const void* d_queries, uint64_t nq, uint64_t knbn,
@@ -595,6 +612,30 @@ int hnsw_b200_blob_info(const void* h, int i, void** dev_ptr, uint64_t* nbytes) 
 int hnsw_b200_blob_commit(void* h) {
   HB_H(h);
   return pass(ix, ix->blob_commit());
+}
+
+// ---- multi-GPU (multi.cu)
+int hnsw_b200_replicate(void* h, int ndev, const int* devices) {
+  HB_H(h);
+  return pass(ix, ix->replicate(ndev, devices));
+}
+int hnsw_b200_replica_count(const void* h) { return h ? (int)((const AnyApi*)h)->ix->replica_count() : 0; }
+int hnsw_b200_nccl_unique_id(uint8_t* id128) {
+  if (!id128) return set_err("NULL argument");
+  return Index::nccl_unique_id(id128) ? set_err("NCCL is not available (libnccl.so.2)") : 0;
+}
+int hnsw_b200_nccl_init(void* h, int nranks, int rank, const uint8_t* id128) {
+  HB_H(h);
+  if (!id128) return set_err("NULL argument");
+  return pass(ix, ix->nccl_init(nranks, rank, id128));
+}
+int hnsw_b200_nccl_broadcast_index(void* h, int root) {
+  HB_H(h);
+  return pass(ix, ix->nccl_broadcast_index(root));
+}
+int hnsw_b200_nccl_allgather(void* h, const void* d_send, void* d_recv, uint64_t bytes_per_rank, void* cuda_stream) {
+  HB_H(h);
+  return pass(ix, ix->nccl_allgather(d_send, d_recv, bytes_per_rank, (cudaStream_t)cuda_stream));
 }
 
 int hnsw_b200_dist_batch(const void* h, const void* queries, uint64_t nq, uint64_t dim, const uint32_t* cand,

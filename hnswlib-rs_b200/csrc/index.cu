@@ -77,6 +77,9 @@ Index::Index(int M_, size_t max_elements_, int max_layer_, int ef_c_, int metric
 }
 
 Index::~Index() {
+  drop_replicas();
+  nccl_destroy();
+  cudaSetDevice(device);
   if (stream_) cudaStreamSynchronize(stream_);
   cudaFree(d_vec_.p); cudaFree(d_adj0_.p); cudaFree(d_adjU_.p); cudaFree(d_upoff_.p); cudaFree(d_adj0d_.p);
   cudaFree(d_adjUd_.p); cudaFree(d_level_.p); cudaFree(d_plevel_.p); cudaFree(d_origin_.p); cudaFree(d_locks_.p);
@@ -297,6 +300,7 @@ int Index::insert_batch(const void* vecs, size_t n_new, size_t stride, const voi
   if (n_new == 0) return 0;
   if (dim == 0) return fail("dimension not set");
   HB_CUDA(cudaSetDevice(device));
+  replicas_stale_ = !replicas_.empty();  // the copies on the other devices are re-broadcast before the next sharded search
   // ---- levels, PointId ranks, upper-list allocation (generate_new_point, hnsw.rs:503-531)
   std::vector<int> lv(n_new);
   size_t need_ul = 0;

@@ -7,7 +7,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <tuple>
 #include <string>
@@ -110,6 +112,19 @@ class Index {
   int blob_info(int i, void** p, uint64_t* bytes) const;
   int blob_commit();
 
+  // ---- multi-GPU (multi.cu).  One process, N devices: replicate() builds a copy of the frozen index on every listed
+  // device (NCCL broadcast) and for_each_shard() runs a batch split into contiguous shards, one worker thread per
+  // device.  One process per GPU: nccl_init() + nccl_broadcast_index() + nccl_allgather().
+  int replicate(int ndev, const int* devices);
+  size_t replica_count() const { return replicas_.size(); }
+  int for_each_shard(size_t nq, const std::function<int(Index*, size_t, size_t)>& run);
+  void drop_replicas();
+  static int nccl_unique_id(unsigned char* out128);
+  int nccl_init(int nranks, int rank, const unsigned char* id128);
+  int nccl_broadcast_index(int root);
+  int nccl_allgather(const void* d_send, void* d_recv, size_t bytes_per_rank, cudaStream_t s);
+  void nccl_destroy();
+
   int dist_batch(const void* queries, size_t nq, int d, const uint32_t* cand, size_t m, float* out);
   int bruteforce(const void* queries, size_t nq, int d, size_t k, uint32_t* out_ids, float* out_dist);
 
@@ -138,6 +153,19 @@ class Index {
   int run_insert_range(size_t first, size_t count, const std::vector<uint16_t>& masks, size_t mask_off);
   template <class T>
   int grow(DevArray<T>& a, size_t need_elems, size_t keep_elems, int fill_byte);
+
+  struct Worker;
+  struct WorkerDeleter {
+    void operator()(Worker* w) const;
+  };
+  int broadcast_to_replicas();
+  std::vector<std::unique_ptr<Index>> replicas_;  // replicas_[i] lives on replica_devices_[i + 1]
+  std::vector<std::unique_ptr<Worker, WorkerDeleter>> workers_;
+  std::vector<void*> comms_;                      // ncclComm_t per device, rank 0 = this index
+  std::vector<int> replica_devices_;
+  bool replicas_stale_ = false;                   // the index changed after the last broadcast
+  void* comm_ = nullptr;                          // ncclComm_t of the one-process-per-GPU mode
+  int nranks_ = 1, rank_ = 0;
 
   bool ok_ = false;
   mutable std::string err_;

@@ -103,6 +103,12 @@ def load_library():
     L.hnsw_b200_blob_count.argtypes = [vp]
     L.hnsw_b200_blob_info.argtypes = [vp, i32, vp, vp]
     L.hnsw_b200_blob_commit.argtypes = [vp]
+    L.hnsw_b200_replicate.argtypes = [vp, i32, vp]
+    L.hnsw_b200_replica_count.argtypes = [vp]
+    L.hnsw_b200_nccl_unique_id.argtypes = [vp]
+    L.hnsw_b200_nccl_init.argtypes = [vp, i32, i32, vp]
+    L.hnsw_b200_nccl_broadcast_index.argtypes = [vp, i32]
+    L.hnsw_b200_nccl_allgather.argtypes = [vp, vp, vp, u64, vp]
     L.hnsw_b200_dist_batch.argtypes = [vp, vp, u64, u64, vp, u64, vp]
     L.hnsw_b200_bruteforce.argtypes = [vp, vp, u64, u64, u64, vp, vp]
     _LIB = L
@@ -376,6 +382,34 @@ class Hnsw:
                                                   C.c_void_p(d_out_ptr), C.c_void_p(d_counts_ptr), int(bool(sync)),
                                                   C.byref(ms) if sync else None))
         return float(ms.value)
+
+    # ---- multi-GPU (include/hnsw_b200.h "Multi-GPU search")
+    def replicate(self, devices):
+        """one process, N devices: copy the index to devices[1:] (NCCL); batched searches are then sharded over them"""
+        d = np.ascontiguousarray(devices, np.int32)
+        self._chk(self._L.hnsw_b200_replicate(self._h, len(d), _p(d)))
+
+    def replica_count(self):
+        return int(self._L.hnsw_b200_replica_count(self._h))
+
+    @staticmethod
+    def nccl_unique_id():
+        """128 bytes of ncclUniqueId (rank 0 creates it, the host hands it to the other ranks)"""
+        buf = np.zeros(128, np.uint8)
+        if load_library().hnsw_b200_nccl_unique_id(_p(buf)) != 0:
+            raise HnswError(last_error())
+        return buf
+
+    def nccl_init(self, nranks, rank, unique_id):
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        self._chk(self._L.hnsw_b200_nccl_init(self._h, int(nranks), int(rank), _p(uid)))
+
+    def nccl_broadcast_index(self, root=0):
+        self._chk(self._L.hnsw_b200_nccl_broadcast_index(self._h, int(root)))
+
+    def nccl_allgather(self, d_send_ptr, d_recv_ptr, bytes_per_rank, cuda_stream=None):
+        self._chk(self._L.hnsw_b200_nccl_allgather(self._h, C.c_void_p(d_send_ptr), C.c_void_p(d_recv_ptr), int(bytes_per_rank),
+                                                   C.c_void_p(cuda_stream or 0)))
 
     def blob_header(self):
         h16 = np.zeros(16, np.uint64)

@@ -288,6 +288,27 @@ int hnsw_b200_blob_count(const void* h);
 int hnsw_b200_blob_info(const void* h, int i, void** dev_ptr, uint64_t* nbytes);
 int hnsw_b200_blob_commit(void* h); /* after the broadcasts: pull the small host mirrors back */
 
+/* ---- Multi-GPU search.  The reference's parallel_search (/root/reference/src/hnsw.rs:1612-1635) fans one
+ * batch out over the host's cores; these entry points fan it out over the GPUs of one box.  NCCL is bound at run time
+ * (libnccl.so.2), used only to copy the frozen index between devices and to gather device-resident answers.
+ *
+ * One process, N devices.  hnsw_b200_replicate copies the index held by `h` (on devices[0], which must be the handle's
+ * device) to devices[1..ndev) with ncclBroadcast.  Afterwards hnsw_b200_search_flat and parallel_search_neighbours_<ty> on
+ * `h` split a batch of >= 64 * ndev queries into ndev contiguous shards; every device copies its shard in, searches it and
+ * writes its slice of the caller's output arrays (input order kept, no gather step).  Inserting into `h` marks the copies
+ * stale; they are re-broadcast before the next sharded search.  ndev = 1 drops the copies. */
+int hnsw_b200_replicate(void* h, int ndev, const int* devices);
+int hnsw_b200_replica_count(const void* h);
+/* One process per GPU.  Rank 0 calls hnsw_b200_nccl_unique_id and hands the 128 bytes to the other ranks by the host's own
+ * means; every rank calls hnsw_b200_nccl_init on its (possibly empty) handle, then hnsw_b200_nccl_broadcast_index(root):
+ * the root's index is copied into every other rank's handle, which must be empty and created with the same
+ * max_nb_connection / distance / element type.  hnsw_b200_nccl_allgather gathers bytes_per_rank bytes of device memory from
+ * every rank into d_recv (nranks * bytes_per_rank) on cuda_stream (NULL = the handle's stream), asynchronously. */
+int hnsw_b200_nccl_unique_id(uint8_t* id128);
+int hnsw_b200_nccl_init(void* h, int nranks, int rank, const uint8_t* id128);
+int hnsw_b200_nccl_broadcast_index(void* h, int root);
+int hnsw_b200_nccl_allgather(void* h, const void* d_send, void* d_recv, uint64_t bytes_per_rank, void* cuda_stream);
+
 /* Stand-alone kernels.  dist_batch: out[nq][m] = dist(queries[i], base[cand[i][j]]) on the index's
  * point store (host pointers).  bruteforce: exact k nearest (ascending) of each query over the
  * index's point store: out_ids are INTERNAL ids. */

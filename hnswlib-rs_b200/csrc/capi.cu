@@ -486,17 +486,17 @@ int hnsw_b200_search_flat(const void* h, const void* queries, uint64_t nq, uint6
     int r = rx->search_host_staged((const char*)queries + first * qrow, nullptr, count, (int)dim, knbn, ef_search, fb, &tmp, &cnts);
     if (r) return r;
     memcpy(out_counts + first, cnts, count * sizeof(int32_t));
-    for (uint64_t i = 0; i < count; ++i)
-      for (uint64_t j = 0; j < knbn; ++j) {
-        const uint64_t s = i * knbn + j, o = (first + i) * knbn + j;
-        const bool valid = (int64_t)j < cnts[i];
-        out_ids[o] = valid ? tmp[s].origin : ~0ull;
-        out_dist[o] = valid ? tmp[s].dist : __builtin_inff();
-        if (out_internal) out_internal[o] = valid ? tmp[s].internal : hb::INVALID_ID;
-        if (out_pid) {  // PointId(level, rank), hnsw.rs:46
-          out_pid[2 * o] = valid ? (int32_t)rx->h_level[tmp[s].internal] : -1;
-          out_pid[2 * o + 1] = valid ? rx->h_rank[tmp[s].internal] : -1;
-        }
+    // the kernel fills the slots beyond a query's count with (~0, +inf, INVALID_ID): plain field copies
+    const uint64_t tot = count * knbn, o0 = first * knbn;
+    for (uint64_t s = 0; s < tot; ++s) out_ids[o0 + s] = tmp[s].origin;
+    for (uint64_t s = 0; s < tot; ++s) out_dist[o0 + s] = tmp[s].dist;
+    if (out_internal)
+      for (uint64_t s = 0; s < tot; ++s) out_internal[o0 + s] = tmp[s].internal;
+    if (out_pid)  // PointId(level, rank), hnsw.rs:46
+      for (uint64_t s = 0; s < tot; ++s) {
+        const uint32_t it = tmp[s].internal;
+        out_pid[2 * (o0 + s)] = it != hb::INVALID_ID ? (int32_t)rx->h_level[it] : -1;
+        out_pid[2 * (o0 + s) + 1] = it != hb::INVALID_ID ? rx->h_rank[it] : -1;
       }
     return 0;
   };

@@ -66,6 +66,7 @@ Index::Index(int M_, size_t max_elements_, int max_layer_, int ef_c_, int metric
   sm_count_ = prop.multiProcessorCount;
   if (const char* k = getenv("HNSW_B200_KERNEL")) kernel_pref_ = strcmp(k, "warp") == 0 ? 1 : (strcmp(k, "team") == 0 ? 2 : 0);
   if (const char* k = getenv("HNSW_B200_TVIS_SHIFT")) tvis_scale_shift_ = atoi(k);
+  if (const char* k = getenv("HNSW_B200_ZERO_COPY")) zero_copy_ = atoi(k) != 0;
   if ((e = cudaMalloc(&d_counter_, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&d_status_, sizeof(int))) != cudaSuccess ||
       (e = cudaMalloc(&d_stats_, 4 * sizeof(unsigned long long))) != cudaSuccess) {
     err_ = std::string("cudaMalloc: ") + cudaGetErrorString(e);
@@ -614,6 +615,24 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
   return 0;
 }
 
+// pointer the device can dereference for a host buffer: pinned (page-locked) memory is mapped into the device's
+// address space under unified addressing; pageable memory is not (nullptr)
+static const void* device_view_of_host(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) return at.devicePointer;
+  return nullptr;
+}
+
+// Host queries in, host answers out.  ZERO-COPY when the memory allows it: a pinned query buffer is read by the
+// kernel itself (each query crosses the bus once, 512 bytes when its warp picks it up, while thousands of other
+// queries are being searched), and the answers are written by the kernel straight into the index's pinned result
+// buffer: no cudaMemcpy before or after the launch, one synchronisation.  Pageable queries and row pointers are
+// gathered into the index's own pinned staging buffer first (the only host-side copy), which the kernel then reads
+// the same way.  zero_copy_ = false (env HNSW_B200_ZERO_COPY=0) restores explicit H2D / D2H copies.
 int Index::search_host_staged(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
                               const uint32_t* filter_bits_host, const NeighbourOut** out, const int32_t** counts) {
   *out = nullptr;
@@ -627,7 +646,7 @@ int Index::search_host_staged(const void* queries, const void* const* rows, size
     if (h_res_) cudaFreeHost(h_res_);
     h_res_ = nullptr;
     h_res_bytes_ = 0;
-    HB_CUDA(cudaMallocHost(&h_res_, out_bytes + cnt_bytes + 16));
+    HB_CUDA(cudaHostAlloc(&h_res_, out_bytes + cnt_bytes + 16, cudaHostAllocMapped | cudaHostAllocPortable));
     h_res_bytes_ = out_bytes + cnt_bytes + 16;
   }
   NeighbourOut* hout = (NeighbourOut*)h_res_;
@@ -635,27 +654,49 @@ int Index::search_host_staged(const void* queries, const void* const* rows, size
   int32_t* hstatus = hcnt + nq;
   *out = hout;
   *counts = hcnt;
-  if (dim == 0) {  // empty index: every answer is empty (hnsw.rs:1498-1503)
+  if (dim == 0) {  // empty index: every answer is empty (hnsw.rs:1498-1500)
     for (size_t i = 0; i < nq; ++i) hcnt[i] = 0;
+    for (size_t i = 0; i < nq * k; ++i) hout[i] = NeighbourOut{~0ull, __builtin_inff(), INVALID_ID};
     return 0;
   }
   const size_t qbytes = nq * (size_t)dim * es;
-  if ((r = ensure_scratch(&d_q_, &d_q_bytes_, qbytes))) return r;
-  if ((r = ensure_scratch(&d_out_, &d_out_bytes_, out_bytes))) return r;
-  if ((r = ensure_scratch(&d_cnt_, &d_cnt_bytes_, cnt_bytes))) return r;
-  if (rows) {
-    if (h_pin_bytes_ < qbytes) {
-      if (h_pin_) cudaFreeHost(h_pin_);
-      h_pin_ = nullptr;
-      h_pin_bytes_ = 0;
-      HB_CUDA(cudaMallocHost(&h_pin_, qbytes));
-      h_pin_bytes_ = qbytes;
+  const void* d_queries = nullptr;  // what the kernel reads
+  const void* host_src = queries;
+  if (rows || !(zero_copy_ && device_view_of_host(queries))) {
+    // gather into pinned staging (rows: one pointer per query, libext.rs parallel_search_neighbours_<ty>)
+    if (rows || !device_view_of_host(queries)) {
+      if (h_pin_bytes_ < qbytes) {
+        if (h_pin_) cudaFreeHost(h_pin_);
+        h_pin_ = nullptr;
+        h_pin_bytes_ = 0;
+        HB_CUDA(cudaHostAlloc(&h_pin_, qbytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        h_pin_bytes_ = qbytes;
+      }
+      unsigned char* st = (unsigned char*)h_pin_;
+      if (rows)
+        for (size_t i = 0; i < nq; ++i) memcpy(st + i * (size_t)dim * es, rows[i], (size_t)dim * es);
+      else
+        memcpy(st, queries, qbytes);
+      host_src = st;
     }
-    unsigned char* st = (unsigned char*)h_pin_;
-    for (size_t i = 0; i < nq; ++i) memcpy(st + i * (size_t)dim * es, rows[i], (size_t)dim * es);
-    HB_CUDA(cudaMemcpyAsync(d_q_, st, qbytes, cudaMemcpyHostToDevice, stream_));
+  }
+  if (zero_copy_) d_queries = device_view_of_host(host_src);
+  if (!d_queries) {
+    if ((r = ensure_scratch(&d_q_, &d_q_bytes_, qbytes))) return r;
+    HB_CUDA(cudaMemcpyAsync(d_q_, host_src, qbytes, cudaMemcpyHostToDevice, stream_));
+    d_queries = d_q_;
+  }
+  NeighbourOut* k_out = nullptr;  // where the kernel writes
+  int32_t* k_cnt = nullptr;
+  const void* dv = zero_copy_ ? device_view_of_host(h_res_) : nullptr;
+  if (dv) {
+    k_out = (NeighbourOut*)dv;
+    k_cnt = (int32_t*)((char*)dv + out_bytes);
   } else {
-    HB_CUDA(cudaMemcpyAsync(d_q_, queries, qbytes, cudaMemcpyHostToDevice, stream_));
+    if ((r = ensure_scratch(&d_out_, &d_out_bytes_, out_bytes))) return r;
+    if ((r = ensure_scratch(&d_cnt_, &d_cnt_bytes_, cnt_bytes))) return r;
+    k_out = (NeighbourOut*)d_out_;
+    k_cnt = (int32_t*)d_cnt_;
   }
   const uint32_t* dfb = nullptr;
   if (filter_bits_host) {
@@ -664,12 +705,14 @@ int Index::search_host_staged(const void* queries, const void* const* rows, size
     HB_CUDA(cudaMemcpyAsync(d_fbits_, filter_bits_host, fb, cudaMemcpyHostToDevice, stream_));
     dfb = (const uint32_t*)d_fbits_;
   }
-  // one enqueue (H2D, kernel, D2H of answers + status), one synchronisation; the slow path (a visited table
-  // overflowed: grow and re-run) is taken only when the status says so
+  // one enqueue (copies if any, kernel, status), one synchronisation; the slow path (a visited table overflowed: grow
+  // and re-run) is taken only when the status says so
   for (int pass = 0; pass < 2; ++pass) {
-    if ((r = search_device(d_q_, nq, k, ef, dfb, (NeighbourOut*)d_out_, (int32_t*)d_cnt_, pass == 1, nullptr))) return r;
-    HB_CUDA(cudaMemcpyAsync(hout, d_out_, out_bytes, cudaMemcpyDeviceToHost, stream_));
-    HB_CUDA(cudaMemcpyAsync(hcnt, d_cnt_, cnt_bytes, cudaMemcpyDeviceToHost, stream_));
+    if ((r = search_device(d_queries, nq, k, ef, dfb, k_out, k_cnt, pass == 1, nullptr))) return r;
+    if (!dv) {
+      HB_CUDA(cudaMemcpyAsync(hout, d_out_, out_bytes, cudaMemcpyDeviceToHost, stream_));
+      HB_CUDA(cudaMemcpyAsync(hcnt, d_cnt_, cnt_bytes, cudaMemcpyDeviceToHost, stream_));
+    }
     HB_CUDA(cudaMemcpyAsync(hstatus, d_status_, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
     HB_CUDA(cudaStreamSynchronize(stream_));
     if (*hstatus == 0) break;

@@ -276,6 +276,13 @@ def run_reference(a, rank, world):
 
 
 # ------------------------------------------------------------------------------------------- our arm
+def note(msg):
+    """progress marks on stderr (BENCH_VERBOSE=1)"""
+    if os.environ.get("BENCH_VERBOSE"):
+        sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}\n")
+        sys.stderr.flush()
+
+
 def shard_bounds(n, rank, world):
     """contiguous shard [lo, hi) of n items for `rank` (sizes differ by at most one)"""
     base, rem = divmod(n, world)
@@ -304,13 +311,17 @@ def run_ours(a, rank, world, local_rank):
         h.insert_flat(X)
         build_s = time.perf_counter() - t0
         del X
+    note('built')
     if multi:
         uid = torch.from_numpy(pkg.Hnsw.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
         dist.broadcast(uid, 0)                     # 128 bytes of ncclUniqueId, by the host's own means
         t0 = time.perf_counter()
+        note('uid exchanged')
         h.nccl_init(world, rank, uid.cpu().numpy())
+        note('comm up')
         h.nccl_broadcast_index(0)                  # ncclBroadcast of header + 9 device arrays, inside the library
         bcast_s = time.perf_counter() - t0
+        note('index broadcast')
         # every replica answers a shared probe batch; the answers must equal rank 0's
         probe = pkg.datagen.make(a.data, 512, a.d, 4242)
         ids = torch.from_numpy(h.search_flat(probe, a.k, a.ef, with_pid=False)[2].astype(np.int64)).cuda()
@@ -321,6 +332,7 @@ def run_ours(a, rank, world, local_rank):
         if int(same.item()) != 1:
             raise RuntimeError("a replica's answers differ from rank 0's")
 
+    note('replicas checked')
     # ---- queries: NB rotating batches per rank, seeded per rank; pinned host copies + device copies
     NB = 4 if nq <= 20000 else 1
     q_host = [torch.from_numpy(pkg.datagen.make(a.data, nq, a.d, 2 + 1000 * rank + b)).pin_memory() for b in range(NB)]
@@ -355,6 +367,7 @@ def run_ours(a, rank, world, local_rank):
         if gather_dev is not None:
             stream.wait_stream(gstream)
 
+    note('buffers ready')
     # ---- one instrumented pass: traversal counters (algorithmic bytes) and recall vs exact brute force
     h.enable_stats(True)
     step_device(0, sync=True)
@@ -375,6 +388,7 @@ def run_ours(a, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    note('instrumented pass done')
     # ---- device-resident: W warm-up steps, then exactly K steps between CUDA events on the launch stream
     for i in range(a.warmup):
         step_device(i)
@@ -390,6 +404,7 @@ def run_ours(a, rank, world, local_rank):
         e1.record(stream)
         barrier()
     dev_ms = e0.elapsed_time(e1)
+    note('device-timed loop done')
     if h.check_status() != 0:
         raise RuntimeError("visited table overflow during the timed region")
     clocks = clk.summary()
@@ -417,30 +432,43 @@ def run_ours(a, rank, world, local_rank):
     torch.cuda.set_stream(torch.cuda.default_stream(dev))
     qh_np = [q.numpy() for q in q_host]
 
-    def timed(fn, steps, warmup):
+    gloo = dist.new_group(backend="gloo") if multi else None
+
+    def host_barrier():
+        # ranks > 0 must not park a spinning NCCL kernel on their GPU while rank 0's process drives that GPU too
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier(group=gloo)
+
+    def timed(fn, steps, warmup, bar=barrier):
         for i in range(warmup):
             fn(i)
-        barrier()
+        bar()
         t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
-        barrier()
+        bar()
         return time.perf_counter() - t0
 
     # (1) every rank calls hnsw_b200_search_flat on its own shard (ids + distances + counts back in host memory)
     per_rank_s = timed(lambda i: h.search_flat(qh_np[i % NB], a.k, a.ef, with_internal=False, with_pid=False), a.steps, a.warmup)
+    note('per-rank e2e done')
     # (2) N > 1: ONE call on rank 0's handle, the library shards the batch over all the box's GPUs
     one_call_s = None
     if multi:
         big = None
+        host_barrier()
         if rank == 0:
+            note('replicating in-process')
             h.replicate(list(range(world)))       # copies on the other GPUs, NCCL inside this process
             big = [torch.from_numpy(pkg.datagen.make(a.data, total_per_step, a.d, 9000 + b)).pin_memory().numpy()
                    for b in range(2 if total_per_step <= 200000 else 1)]
         one_call_s = timed(lambda i: h.search_flat(big[i % len(big)], a.k, a.ef, with_internal=False, with_pid=False)
-                           if rank == 0 else None, a.steps, a.warmup)
+                           if rank == 0 else None, a.steps, a.warmup, bar=host_barrier)
         if rank == 0:
             h.replicate([dev])
+        host_barrier()
+    note('one-call e2e done')
     # (3) N = 1: the reference's own entry point, pageable row pointers, one malloc'ed Neighbourhood per query
     rowptr_s = None
     if not multi and nq <= 100000:

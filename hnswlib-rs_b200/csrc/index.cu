@@ -78,6 +78,7 @@ Index::Index(int M_, size_t max_elements_, int max_layer_, int ef_c_, int metric
 }
 
 Index::~Index() {
+  DeviceRestore keep;
   drop_replicas();
   nccl_destroy();
   cudaSetDevice(device);

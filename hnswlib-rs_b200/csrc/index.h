@@ -30,6 +30,16 @@ struct SplitMix64 {
   double unif() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
 };
 
+// restores the calling thread's current device on scope exit (the library switches devices when it works on replicas;
+// a host that tracks the current device itself, e.g. torch, must find it unchanged after every call)
+struct DeviceRestore {
+  int prev = -1;
+  DeviceRestore() { cudaGetDevice(&prev); }
+  ~DeviceRestore() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 template <class T>
 struct DevArray {  // growable device array, contents preserved on growth
   T* p = nullptr;

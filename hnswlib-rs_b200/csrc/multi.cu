@@ -129,6 +129,7 @@ struct Index::Worker {
 void Index::WorkerDeleter::operator()(Worker* w) const { delete w; }
 
 void Index::drop_replicas() {
+  DeviceRestore keep;
   workers_.clear();
   if (nccl().ok)
     for (void* c : comms_)
@@ -140,6 +141,7 @@ void Index::drop_replicas() {
 
 // broadcast the nine blobs of `this` (communicator rank 0) to the replicas (ranks 1..), then rebuild their host mirrors
 int Index::broadcast_to_replicas() {
+  DeviceRestore keep;
   NcclApi& nc = nccl();
   uint64_t header[16];
   blob_header(header);
@@ -186,6 +188,7 @@ int Index::broadcast_to_replicas() {
 }
 
 int Index::replicate(int ndev, const int* devices) {
+  DeviceRestore keep;
   if (ndev < 1 || !devices) return fail("replicate: need at least one device");
   if (devices[0] != device) return fail("replicate: devices[0] must be the device that holds the index");
   NcclApi& nc = nccl();
@@ -220,6 +223,7 @@ int Index::replicate(int ndev, const int* devices) {
 
 // Contiguous shards, one per device; shard 0 runs on the calling thread.  `run` is called as run(index, first, count).
 int Index::for_each_shard(size_t nq, const std::function<int(Index*, size_t, size_t)>& run) {
+  DeviceRestore keep;
   if (replicas_stale_) {
     int r = broadcast_to_replicas();
     if (r) return r;
@@ -253,6 +257,7 @@ int Index::nccl_unique_id(unsigned char* out128) {
 }
 
 int Index::nccl_init(int nranks, int rank, const unsigned char* id128) {
+  DeviceRestore keep;
   NcclApi& nc = nccl();
   if (!nc.ok) return fail("nccl_init: " + nc.why);
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail("nccl_init: bad rank");
@@ -272,6 +277,7 @@ int Index::nccl_init(int nranks, int rank, const unsigned char* id128) {
 }
 
 int Index::nccl_broadcast_index(int root) {
+  DeviceRestore keep;
   NcclApi& nc = nccl();
   if (!comm_) return fail("nccl_broadcast_index: call hnsw_b200_nccl_init first");
   if (root < 0 || root >= nranks_) return fail("nccl_broadcast_index: bad root");
@@ -304,6 +310,7 @@ int Index::nccl_broadcast_index(int root) {
 }
 
 int Index::nccl_allgather(const void* d_send, void* d_recv, size_t bytes_per_rank, cudaStream_t s) {
+  DeviceRestore keep;
   NcclApi& nc = nccl();
   if (!comm_) return fail("nccl_allgather: call hnsw_b200_nccl_init first");
   HB_CUDA(cudaSetDevice(device));

@@ -106,3 +106,29 @@ def test_replicated_search_equals_one_gpu(pkg, po):
     assert h.replica_count() == 0
     for a, b in zip(h.search_flat(Q, 10, 64), got):
         assert np.array_equal(a, b)
+
+
+def test_calls_leave_the_current_device_alone(pkg, po):
+    """a host that tracks the current device itself (torch) must find it unchanged after replicate / search / drop"""
+    import torch
+    L = pkg.load_library()
+    if L.hnsw_b200_device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    X, o, h = build_pair(pkg, po, 5000, 16, 8, 40, "DistL2")
+    Q = pkg.datagen.uniform(512, 16, 3)
+    torch.cuda.set_device(0)
+    rt = _cudart()
+    cur = ctypes.c_int(-1)
+
+    def current():
+        assert rt.cudaGetDevice(ctypes.byref(cur)) == 0
+        return cur.value
+    assert current() == 0
+    h.replicate([0, 1])
+    assert current() == 0
+    h.search_flat(Q, 5, 32)
+    assert current() == 0
+    h.replicate([0])
+    assert current() == 0
+    del h
+    assert current() == 0

@@ -1,6 +1,7 @@
 // extern "C" surface of libhnsw_b200.so: the reference's libext.rs symbols (f32) + extensions.
 // Declarations and the reference file:line each one replaces are in include/hnsw_b200.h.
 #include <cstdlib>
+#include <exception>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -260,7 +261,17 @@ struct HnswIo {
   std::string dir, basename;
 };
 
+static void* load_any_unguarded(HnswIo* io, int dtype, int metric);
+// nothing may unwind through the C boundary: a dump that makes an allocation fail returns NULL like the reference does
 static void* load_any(HnswIo* io, int dtype, int metric) {
+  try {
+    return load_any_unguarded(io, dtype, metric);
+  } catch (const std::exception& e) {
+    set_err(std::string("load_hnswdump: ") + e.what());
+    return nullptr;
+  }
+}
+static void* load_any_unguarded(HnswIo* io, int dtype, int metric) {
   if (!io) {
     set_err("load_hnswdump: NULL HnswIo");
     return nullptr;

@@ -72,7 +72,9 @@ __device__ __forceinline__ void search_layer_filtered(const GraphView& g, const 
     // entry point fails the filter, ef == 1 and it was retained away); we return the empty W instead.
     if (W.n == 0) break;
     const uint64_t fkey = W.w[W.n - 1] & ~1ull;
-    if (best > fkey && W.n >= ef) {  // 981, 994-1000: retain only the points passing the filter
+    // 981: the reference compares DISTANCES here (-(c.dist) > f.dist); with equal distances a larger id must not
+    // trigger the retain pass (Hamming / Jaccard / integer L1 tie often)
+    if ((best >> 32) > (fkey >> 32) && W.n >= ef) {  // 994-1000: retain only the points passing the filter
       int out = 0;
       for (int b = 0; b < W.n; b += 32) {
         const int i = b + lane;

@@ -104,6 +104,7 @@ static bool exists(const std::string& p) {
 
 // ------------------------------------------------------------------------------------------------ dump
 int Index::file_dump(const std::string& dir, const std::string& basename_default, bool overwrite, std::string* used) {
+  if (poisoned_) return fail(poison_msg_);
   if (max_layer != MAX_LAYERS) return fail("dump of Description, nb_layer != NB_MAX_LAYER (hnswio.rs:893-896)");
   if (n == 0 || entry == INVALID_ID) return fail("entry point not initialized (hnswio.rs:1323-1325)");
   // DumpInit::new (hnswio.rs:150-236): keep an existing data file when overwrite is false
@@ -283,6 +284,13 @@ int Index::load_dump(const std::string& dir, const std::string& basename) {
   const uint64_t ddim = d.get<uint64_t>();
   if (ddim != de.dimension) return bail("data dimension differs between graph and data files");
   const size_t N = (size_t)de.nb_point, D = (size_t)de.dimension, ES = (size_t)dtype_size(dtype);
+  {  // a corrupt header must not size the allocations below: every point costs >= 20 + D*ES bytes of .hnsw.data and
+     // >= 17 bytes of .hnsw.graph
+    struct stat sd, sg;
+    if (stat(dpath.c_str(), &sd) != 0 || stat(gpath.c_str(), &sg) != 0) return bail("cannot stat the dump files");
+    if (D == 0 || D > ((size_t)1 << 24) || N > (size_t)sd.st_size / (20 + D * ES) + 1 || N > (size_t)sg.st_size / 17 + 1)
+      return bail("dump header (nb_point, dimension) is inconsistent with the file sizes");
+  }
   const int nb_layer = g.get<uint8_t>();
   if (nb_layer > MAX_LAYERS) return bail("nb_layer > 16");
   struct Nb {

@@ -251,6 +251,32 @@ int Index::grow_plevel(uint32_t id, int new_pl) {
   return 0;
 }
 
+// shared-memory footprint of the insert kernel for this (dimension, ef_construction, M): checked before an insert
+// changes any state
+int Index::check_insert_fit() {
+  int qk = queue_kind(ef_c, metric, dtype);
+  if (qk != 0 && qk < 104) qk = 104;
+  const size_t smem = insert_smem_per_warp(row_bytes / 16, ef_c, 2 * M, queue_slots(qk, ef_c)) * (BUILD_THREADS / 32);
+  if (smem > 220 * 1024) return fail("ef_construction / dimension too large for the insert kernel's shared memory");
+  return 0;
+}
+
+// forget the points [keep, n): they were stored but never linked (a failed insert call)
+void Index::rollback_points(size_t keep) {
+  n = keep;
+  h_level.resize(keep);
+  h_plevel.resize(keep);
+  h_rank.resize(keep);
+  h_origin.resize(keep);
+  h_upoff.resize(keep);
+  for (int l = 0; l < MAX_LAYERS; ++l) layer_count[l] = 0;
+  n_ul = 0;
+  for (size_t p = 0; p < keep; ++p) {
+    layer_count[h_level[p]]++;
+    if (h_plevel[p] > 0) n_ul = std::max<size_t>(n_ul, (size_t)h_upoff[p] + h_plevel[p]);
+  }
+}
+
 int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16_t>& masks, size_t mask_off) {
   (void)masks;
   InsertParams p;
@@ -301,7 +327,10 @@ int Index::insert_batch(const void* vecs, size_t n_new, size_t stride, const voi
                         const int32_t* levels) {
   if (n_new == 0) return 0;
   if (dim == 0) return fail("dimension not set");
+  if (poisoned_) return fail(poison_msg_);
   HB_CUDA(cudaSetDevice(device));
+  int fit = check_insert_fit();
+  if (fit) return fit;
   replicas_stale_ = !replicas_.empty();  // the copies on the other devices are re-broadcast before the next sharded search
   // ---- levels, PointId ranks, upper-list allocation (generate_new_point, hnsw.rs:503-531)
   std::vector<int> lv(n_new);
@@ -396,8 +425,20 @@ int Index::insert_batch(const void* vecs, size_t n_new, size_t stride, const voi
         break;
       }
     }
-    if (promo && (r = grow_plevel(entry, lv[done]))) return r;  // old entry point gains lists up to the new top
-    if ((r = run_insert_range(id, nb, masks, done))) return r;
+    r = promo ? grow_plevel(entry, lv[done]) : 0;  // old entry point gains lists up to the new top
+    if (!r) r = run_insert_range(id, nb, masks, done);
+    if (r) {
+      // the batches before this one are fully linked and stay; the rest of the call is forgotten.  A CUDA failure can
+      // leave half-written links behind: the handle then refuses further work instead of serving a broken graph.
+      const std::string why = err_;
+      if (r == -2) {
+        poisoned_ = true;
+        poison_msg_ = "index unusable after a CUDA failure during insert: " + why;
+      }
+      rollback_points(id);
+      err_ = why + " (insert rolled back to " + std::to_string(id) + " points)";
+      return r;
+    }
     if (promo) {
       entry = (uint32_t)id;
       entry_level = lv[done];
@@ -511,6 +552,7 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
                          NeighbourOut* d_out, int32_t* d_counts, bool sync, float* kernel_ms) {
   if (nq == 0) return 0;
   if (k == 0) return fail("knbn must be positive");
+  if (poisoned_) return fail(poison_msg_);
   HB_CUDA(cudaSetDevice(device));
   if (dim == 0) {  // empty index: every answer is empty (hnsw.rs:1498-1503)
     HB_CUDA(cudaMemsetAsync(d_counts, 0, nq * sizeof(int32_t), stream_));

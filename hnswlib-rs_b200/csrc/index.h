@@ -161,6 +161,8 @@ class Index {
   int ensure_scratch(void** p, size_t* cur, size_t need);
   int grow_plevel(uint32_t id, int new_plevel);
   int run_insert_range(size_t first, size_t count, const std::vector<uint16_t>& masks, size_t mask_off);
+  int check_insert_fit();
+  void rollback_points(size_t keep);
   template <class T>
   int grow(DevArray<T>& a, size_t need_elems, size_t keep_elems, int fill_byte);
 
@@ -178,6 +180,8 @@ class Index {
   int nranks_ = 1, rank_ = 0;
 
   bool ok_ = false;
+  bool poisoned_ = false;  // a CUDA failure interrupted an insert: the graph may hold half-written links
+  std::string poison_msg_;
   mutable std::string err_;
   cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;

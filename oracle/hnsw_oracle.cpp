@@ -233,6 +233,7 @@ class Index {
       const Item& f = W.peek();  // 973
       bool stop;
       if (mode == MODE_STD) stop = (-c.kd) > f.kd;  // 981
+      else if (has_filter) stop = (-c.kd) > f.kd;  // with a filter the rule only prunes W: distances, as the reference
       else stop = ItemCmp{MODE_DET, false}(Item{-c.kd, c.id}, f) > 0;
       if (stop) {
         if (!has_filter) return W;  // 992-993

@@ -153,3 +153,43 @@ def test_row_pointer_entry_points_for_u8(pkg, po):
     assert h.get_nb_point() == 400
     par = h.parallel_search([X[3], X[399]], 2, 32)
     assert par[0][0].d_id == 503 and par[0][0].distance == 0.0 and par[1][0].d_id == 899
+
+
+def test_failed_insert_leaves_a_consistent_index(pkg):
+    """An insert call that cannot run (here: ef_construction far beyond the insert kernel's shared memory) is refused
+    BEFORE it changes anything: the point count, the dump and later searches see only the points that are linked."""
+    h = pkg.Hnsw(16, 1000, 16, 40, "DistL2")
+    X = pkg.datagen.uniform(300, 16, 1)
+    h.insert_flat(X)
+    before = h.search_flat(X[:20], 3, 16)
+    bad = pkg.Hnsw(16, 1000, 16, 200000, "DistL2")      # ef_construction = 200 000: 1.6 MB of queue per warp
+    with pytest.raises(pkg.HnswError):
+        bad.insert_flat(X[:50])
+    assert bad.get_nb_point() == 0                       # nothing of the refused call is counted
+    o, d, it, _, c = bad.search_flat(X[:4], 2, 8)
+    assert np.all(c == 0)
+    # the healthy handle is unaffected, and a refused dimension mismatch changes nothing either
+    with pytest.raises(pkg.HnswError):
+        h.insert_flat(pkg.datagen.uniform(5, 17, 2))
+    assert h.get_nb_point() == 300
+    for a, b in zip(before, h.search_flat(X[:20], 3, 16)):
+        assert np.array_equal(a, b)
+
+
+def test_corrupt_dump_header_returns_null(pkg, tmp_path):
+    """nb_point / dimension in a damaged header must not size allocations (the reference returns an error, hnswio.rs)"""
+    h = pkg.Hnsw(8, 100, 16, 40, "DistL2")
+    h.insert_flat(pkg.datagen.uniform(60, 8, 1))
+    base = h.file_dump(tmp_path, "hdr")
+    g = tmp_path / (base + ".hnsw.graph")
+    raw = bytearray(g.read_bytes())
+    # Description: magic u32, version... nb_point is a u64 field; flip the high bytes of every 8-byte word that holds 60
+    hit = 0
+    for off in range(0, min(len(raw), 200) - 8):
+        if int.from_bytes(raw[off:off + 8], "little") == 60:
+            raw[off + 5] = 0x7F
+            hit += 1
+    assert hit >= 1
+    g.write_bytes(bytes(raw))
+    with pytest.raises(pkg.HnswError):
+        pkg.Hnsw.load(tmp_path, base, "DistL2")

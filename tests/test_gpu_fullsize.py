@@ -64,3 +64,60 @@ def test_fullsize_recall_and_oracle_spotcheck(pkg, po, c2):
     orc.import_graph(X, og, lv, entry, {l: h.export_layer(l) for l in range(int(lv.max()) + 1)})
     oo, od, oi, _, oc = orc.search_batch(Q[:300], 10, 64, nthreads=8)
     assert np.array_equal(oi, it[:300]) and np.array_equal(od.view(np.uint32), d[:300].view(np.uint32))
+
+
+def _oracle_on_gpu_graph(po, h, X, M, efc, metric, d):
+    """the GPU-built graph, imported into the oracle (MODE_DET + the kernels' summation order)"""
+    lv, rk, og, entry = h.export_points()
+    orc = po.Oracle(M, len(X), 16, efc, metric, d, mode=po.MODE_DET, order=po.ORDER_GPU)
+    orc.import_graph(X, og, lv, entry, {l: h.export_layer(l) for l in range(int(lv.max()) + 1)})
+    return orc
+
+
+def test_c4_mnist_shape_full_size_all_queries_equal_oracle(pkg, po):
+    """BASELINE.json configs[3] at full size: 60 000 x 784 f32 L2, M=32, ef=200, all 10 000 queries.  The oracle searches
+    the SAME graph: ids, distance bits and the traversal counters must be equal."""
+    import os
+    n, d, M, efc, k, ef = 60000, 784, 32, 400, 10, 200
+    X = pkg.datagen.uniform(n, d, 1)
+    h = pkg.Hnsw(M, n, 16, efc, "DistL2")
+    h.insert_flat(X)
+    Q = pkg.datagen.uniform(10000, d, 2)
+    h.enable_stats(True)
+    h.get_stats()
+    go, gd, gi, _, gc = h.search_flat(Q, k, ef)
+    cg = h.get_stats()
+    orc = _oracle_on_gpu_graph(po, h, X, M, efc, "DistL2", d)
+    orc.counters()
+    oo, od, oi, _, oc = orc.search_batch(Q, k, ef, nthreads=os.cpu_count() or 8)
+    co = orc.counters()
+    assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    for key in ("evals", "expansions", "adj_read"):
+        assert cg[key] == co[key], (key, cg, co)
+    bi, bd = h.bruteforce(Q[:500], k)
+    rec = np.mean([len(set(gi[i].tolist()) & set(bi[i].tolist())) / k for i in range(500)])
+    print("C4 recall@10 at ef=200:", rec)
+    assert rec > 0.5   # iid uniform 784-d is adversarial for any graph index (SURVEY 8d); the parity above is the test
+
+
+@pytest.mark.parametrize("metric", ["DistDot", "DistCosine"])
+def test_c3_glove_shape_full_size_oracle_spotcheck(pkg, po, metric):
+    """BASELINE.json configs[2] at full size: 1 183 514 x 25 unit vectors, M=24, ef=128, with the metric the config names
+    (DistCosine) and the one the reference's example actually runs on normalised data (DistDot)."""
+    n, d, M, efc, k, ef = 1183514, 25, 24, 200, 10, 128
+    X = pkg.datagen.unit(n, d, 1)
+    h = pkg.Hnsw(M, n, 16, efc, metric)
+    h.insert_flat(X)
+    Q = pkg.datagen.unit(10000, d, 2)
+    go, gd, gi, _, gc = h.search_flat(Q, k, ef)
+    assert np.all(gc == k) and np.all(np.diff(gd, axis=1) >= 0) and np.all(gd >= 0)
+    go2, gd2, gi2, _, _ = h.search_flat(Q, k, ef)
+    assert np.array_equal(gi, gi2) and np.array_equal(gd.view(np.uint32), gd2.view(np.uint32))
+    bi, bd = h.bruteforce(Q[:1000], k)
+    rec = np.mean([len(set(gi[i].tolist()) & set(bi[i].tolist())) / k for i in range(1000)])
+    print(f"C3 {metric} recall@10 at ef=128:", rec)
+    assert rec > 0.8
+    orc = _oracle_on_gpu_graph(po, h, X, M, efc, metric, d)
+    oo, od, oi, _, oc = orc.search_batch(Q[:300], k, ef, nthreads=8)
+    assert np.array_equal(oi, gi[:300]) and np.array_equal(od.view(np.uint32), gd[:300].view(np.uint32))

@@ -223,3 +223,38 @@ def test_integer_det_vs_std_tie_report(pkg, po):
     same_d = np.mean(np.all(a[1] == b[1], axis=1))
     print("fraction of queries with identical distance lists under std vs det tie rules:", same_d)
     assert same_d > 0.8
+
+
+PROB_METRICS = ["DistHellinger", "DistJeffreys", "DistJensenShannon"]
+
+
+@pytest.mark.parametrize("metric", PROB_METRICS)
+def test_probability_metrics_match_reference_order_oracle(pkg, po, metric):
+    """Hellinger / Jeffreys / Jensen-Shannon (init_hnsw_f32 accepts them, libext.rs:468-520): the device uses logf / sqrtf
+    and the kernels' summation order, the literal-reference oracle std::log and AVX2-shaped sums, so the bar is the
+    tolerance BASELINE.json states (1e-5 relative, recall within 1e-3), not bit equality."""
+    n, d, M, efc, k, ef = 3000, 32, 12, 80, 10, 48
+    rng = np.random.default_rng(5)
+    X = rng.random((n, d), dtype=np.float32) + np.float32(1e-3)
+    X /= X.sum(1, keepdims=True)                      # discrete probability vectors, strictly positive
+    Q = rng.random((300, d), dtype=np.float32) + np.float32(1e-3)
+    Q /= Q.sum(1, keepdims=True)
+    o = po.Oracle(M, n, 16, efc, metric, d, mode=po.MODE_STD, order=po.ORDER_REF)
+    o.insert_batch(X)
+    lv, rk, og = o.export_points()
+    h = pkg.Hnsw(M, n, 16, efc, metric)
+    h.import_graph(X, og, lv, o.entry, oracle_layers(o))
+    # the distance kernel alone: every value within 1e-5 relative (absolute 1e-7 near zero) of the reference-order sum
+    cand = rng.integers(0, n, (300, 40)).astype(np.uint32)
+    got = h.dist_batch(Q, cand)
+    for i in range(0, 300, 7):
+        want = np.array([po.dist(Q[i], X[j], metric, po.ORDER_REF) for j in cand[i]], np.float32)
+        assert np.allclose(got[i], want, rtol=1e-5, atol=1e-7), (metric, i)
+    # the search on the same graph: recall within 1e-3 of the oracle's, distances of shared answers within 1e-5
+    oo, od, oi, _, oc = o.search_batch(Q, k, ef)
+    go, gd, gi, _, gc = h.search_flat(Q, k, ef)
+    ti, td = po.bruteforce(X, Q, k, metric)
+    assert abs(recall_ids(oi, oc, ti) - recall_ids(gi, gc, ti)) <= 1e-3
+    same = oi == gi
+    assert same.mean() > 0.99
+    assert np.allclose(gd[same], od[same], rtol=1e-5, atol=1e-7)

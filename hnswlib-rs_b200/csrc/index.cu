@@ -64,8 +64,7 @@ Index::Index(int M_, size_t max_elements_, int max_layer_, int ef_c_, int metric
   }
   own_stream_ = stream_;
   sm_count_ = prop.multiProcessorCount;
-  if (const char* k = getenv("HNSW_B200_KERNEL")) kernel_pref_ = strcmp(k, "warp") == 0 ? 1 : (strcmp(k, "team") == 0 ? 2 : 0);
-  if (const char* k = getenv("HNSW_B200_TVIS_SHIFT")) tvis_scale_shift_ = atoi(k);
+  if (const char* k = getenv("HNSW_B200_KERNEL")) kernel_pref_ = strcmp(k, "warp") == 0 ? 1 : 0;
   if (const char* k = getenv("HNSW_B200_ZERO_COPY")) zero_copy_ = atoi(k) != 0;
   if ((e = cudaMalloc(&d_counter_, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&d_status_, sizeof(int))) != cudaSuccess ||
       (e = cudaMalloc(&d_stats_, 4 * sizeof(unsigned long long))) != cudaSuccess) {
@@ -85,7 +84,7 @@ Index::~Index() {
   if (stream_) cudaStreamSynchronize(stream_);
   cudaFree(d_vec_.p); cudaFree(d_adj0_.p); cudaFree(d_adjU_.p); cudaFree(d_upoff_.p); cudaFree(d_adj0d_.p);
   cudaFree(d_adjUd_.p); cudaFree(d_level_.p); cudaFree(d_plevel_.p); cudaFree(d_origin_.p); cudaFree(d_locks_.p);
-  cudaFree(vis_.tab); cudaFree(vis_.epoch); cudaFree(tvis_.tab); cudaFree(tvis_.epoch); cudaFree(d_counter_); cudaFree(d_status_); cudaFree(d_stats_);
+  cudaFree(vis_.tab); cudaFree(vis_.epoch); cudaFree(svis_.tab); cudaFree(svis_.epoch); cudaFree(d_counter_); cudaFree(d_status_); cudaFree(d_stats_);
   cudaFree(d_q_); cudaFree(d_out_); cudaFree(d_cnt_); cudaFree(d_fbits_); cudaFree(d_mask_); cudaFree(d_cbuf_);
   if (h_pin_) cudaFreeHost(h_pin_);
   if (h_res_) cudaFreeHost(h_res_);
@@ -148,9 +147,9 @@ int Index::ensure_upper(size_t need) {
   return 0;
 }
 
-// A pool is laid out as [slots][cap] for the (slots, cap) it was last sized for.  The warp kernels (insert, filtered and
-// generic search) share one pool; the team kernel owns another, so that its small L2-resident tables are not
-// inflated by the insert path's large ones.
+// A pool is laid out as [slots][cap] for the (slots, cap) it was last sized for.  Insert and filtered search share one
+// pool (large tables); unfiltered searches own another, so that their small L2-resident tables are not inflated by
+// the insert path's (4x larger: ef_construction instead of ef).
 int Index::ensure_visited(VisitedPool& v, size_t slots, size_t cap_entries) {
   if (slots <= v.slots && cap_entries <= v.cap) return 0;
   size_t ns = std::max(slots, v.slots), nc = std::max(cap_entries, v.cap);
@@ -578,47 +577,39 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
   p.stats = stats_on_ ? d_stats_ : nullptr;
   p.status = d_status_;
   const bool filtered = d_filter_bits != nullptr;
-  // kernel choice: the team kernel (8 lanes per query, search_team.cu) whenever it applies, else one warp per query
-  // kernel choice: lean (one warp per query, search_lean.cu) whenever it applies, else the generic warp kernel;
-  // the team kernel (8 lanes per query, search_team.cu) on request (HNSW_B200_KERNEL=team)
-  const bool fast_ok = !filtered && entry != INVALID_ID && team_op_supported(metric, dtype) && team_eligible(p.g.d4, p.ef);
-  const bool team = fast_ok && kernel_pref_ == 2;
-  const bool lean = fast_ok && kernel_pref_ == 0;
-  p.q_kind = (filtered || team || lean) ? 0 : queue_kind(p.ef, metric, dtype);
-  p.q_smem = (team || lean) ? team_queue_slots(p.ef) : queue_slots(p.q_kind, p.ef);
-  size_t spw = team ? 4 * team_smem_per_team(p.g.d4, p.q_smem)
-                    : (lean ? lean_smem_per_warp(p.q_smem) : search_smem_per_warp(p.g.d4, p.q_smem));
+  // kernel choice: lean (search_lean.cuh) whenever it applies, else the generic warp kernel (search.cu / filter.cu)
+  const bool lean = !filtered && kernel_pref_ == 0 && entry != INVALID_ID && lean_eligible(p.g.d4, p.ef) && lean_op_supported(metric, dtype);
+  p.q_kind = (filtered || lean) ? 0 : queue_kind(p.ef, metric, dtype);
+  p.q_smem = lean ? lean_queue_slots(p.ef) : queue_slots(p.q_kind, p.ef);
+  size_t spw = lean ? lean_smem_per_warp(p.q_smem) : search_smem_per_warp(p.g.d4, p.q_smem);
   p.smem_per_warp = (int)spw;
-  const int wpb = (team ? TEAM_THREADS : (lean ? LEAN_THREADS : SEARCH_THREADS)) / 32;
-  const int qpw = team ? 4 : 1;  // queries in flight per warp
+  const int wpb = (lean ? LEAN_THREADS : SEARCH_THREADS) / 32;
   const size_t smem = spw * wpb;
   if (smem > 220 * 1024) return fail("ef / dimension too large for the search kernel's shared memory");
   p.cbuf = nullptr;
   p.ccap = 0;
   int bps = 0;
   {
-    const auto key = std::make_tuple(team ? 2 : (lean ? 3 : (int)filtered), (team || lean) ? p.q_smem : p.q_kind, p.g.d4, smem);
+    const auto key = std::make_tuple(lean ? 3 : (int)filtered, lean ? p.q_smem : p.q_kind, p.g.d4, smem);
     auto it = occ_cache_.find(key);
     if (it != occ_cache_.end()) {
       bps = it->second;
     } else {
-      if (team) HB_CUDA(launch_search_team(p, metric, dtype, 0, smem, stream_, true, &bps));
-      else if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, 0, smem, stream_, true, &bps));
+      if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, 0, smem, stream_, true, &bps));
       else if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, 0, smem, stream_, true, &bps));
       else HB_CUDA(launch_search(p, metric, dtype, 0, smem, stream_, true, &bps));
       occ_cache_[key] = bps;
     }
   }
   if (bps < 1) return fail("search kernel does not fit on an SM");
-  const size_t per_cta = (size_t)wpb * qpw;
+  const size_t per_cta = (size_t)wpb;
   int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (nq + per_cta - 1) / per_cta);
   const int deg = layer0 == 0 ? 2 * M : M;
-  // visited-table capacity per query slot.  A search inserts ~ (ef + a few) * (fresh neighbours per expansion) ids; the
-  // tables are meant to stay in L2, so the team kernel (2-4x more slots in flight) starts from half the warp kernel's
-  // size.  An overflow is detected in the kernel and the batch re-run with doubled tables.
-  size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)(team ? 1 : 2) * (p.ef + 16) * deg));
-  if (team && tvis_scale_shift_ != 0) vcap = tvis_scale_shift_ > 0 ? vcap << tvis_scale_shift_ : std::max<size_t>(1024, vcap >> -tvis_scale_shift_);
-  VisitedPool& pool = team ? tvis_ : vis_;
+  // visited-table capacity per query slot: a search inserts ~ (ef + a few) * (fresh neighbours per expansion) ids.  An
+  // overflow is detected in the kernel and the batch re-run with doubled tables.  Searches have their own pool: the
+  // insert path's tables are 4x larger (ef_construction) and would push the search's out of L2.
+  size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)2 * (p.ef + 16) * deg));
+  VisitedPool& pool = filtered ? vis_ : svis_;
   for (int attempt = 0;; ++attempt) {
     int r;
     if (filtered) {
@@ -637,8 +628,7 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
     }
     HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
     HB_CUDA(cudaEventRecord(ev0_, stream_));
-    if (team) HB_CUDA(launch_search_team(p, metric, dtype, grid, smem, stream_, false, nullptr));
-    else if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, grid, smem, stream_, false, nullptr));
+    if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, grid, smem, stream_, false, nullptr));
     else if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, grid, smem, stream_, false, nullptr));
     else HB_CUDA(launch_search(p, metric, dtype, grid, smem, stream_, false, nullptr));
     HB_CUDA(cudaEventRecord(ev1_, stream_));

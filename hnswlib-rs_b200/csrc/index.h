@@ -195,11 +195,10 @@ class Index {
   DevArray<uint64_t> d_origin_;
   DevArray<int> d_locks_;
 
-  // visited tables: vis_ serves the warp-per-query kernels, tvis_ the team kernel
-  VisitedPool vis_, tvis_;
-  int kernel_pref_ = 0;        // env HNSW_B200_KERNEL (A/B measurements): 0 = automatic (lean), 1 = "warp" (generic kernel), 2 = "team"
+  // visited tables: vis_ serves insert and filtered search, svis_ the unfiltered searches
+  VisitedPool vis_, svis_;
+  int kernel_pref_ = 0;        // env HNSW_B200_KERNEL=warp (A/B measurements): 1 = always the generic warp kernel
   bool zero_copy_ = true;      // env HNSW_B200_ZERO_COPY=0: explicit H2D / D2H copies instead of kernel access to pinned host memory
-  int tvis_scale_shift_ = 0;   // env HNSW_B200_TVIS_SHIFT: scale the team kernel's visited tables by 2^shift (measurements)
 
   // small device scratch
   unsigned int* d_counter_ = nullptr;

@@ -18,8 +18,6 @@ constexpr int LEAN_THREADS = 128;     // lean kernel (search_lean.cu): 4 warps =
 #define HB_LEAN_BLOCKS 7
 #endif
 constexpr int LEAN_MIN_BLOCKS = HB_LEAN_BLOCKS;  // 7 CTAs x 4 warps = 28 warps per SM, <= 72 registers per thread (measured: 6, 7, 8 CTAs within 3 %)
-constexpr int TEAM_THREADS = 32;     // team kernel (search_team.cu): one warp per CTA = 4 queries of 8 lanes each
-constexpr int TEAM_MIN_BLOCKS = 16;  // 16 warps x 4 teams = 64 queries resident per SM (9 472 per B200), <= 128 registers per thread
 
 // One answer slot.  Same 16-byte layout as the reference's #[repr(C)] Neighbour_api {id: usize, d: f32}
 // (/root/reference/src/libext.rs:64-71); the internal id rides in what is tail padding there.
@@ -72,12 +70,11 @@ inline size_t search_smem_per_warp(int d4, int q_smem) {
   return (b + 127) & ~(size_t)127;
 }
 
-// ---- team kernel (search_team.cu): eligibility and shared-memory footprint
+// ---- lean kernel (search_lean.cuh): eligibility and shared-memory footprint
 // rows of 128 / 256 / 512 bytes (compile-time chunk count), ef <= 128, no filter
-inline int team_queue_slots(int ef) { return ef <= 64 ? 64 : (ef <= 128 ? 128 : 0); }
-inline bool team_eligible(int d4, int ef) { return (d4 == 8 || d4 == 16 || d4 == 32) && team_queue_slots(ef) != 0; }
+inline int lean_queue_slots(int ef) { return ef <= 64 ? 64 : (ef <= 128 ? 128 : 0); }
+inline bool lean_eligible(int d4, int ef) { return (d4 == 8 || d4 == 16 || d4 == 32) && lean_queue_slots(ef) != 0; }
 inline size_t lean_smem_per_warp(int qc) { return (size_t)qc * 8 + 256; }
-inline size_t team_smem_per_team(int d4, int qc) { return (size_t)qc * 8 + 128 + (size_t)d4 * 16; }
 
 struct InsertParams {
   GraphView g;
@@ -112,8 +109,10 @@ cudaError_t launch_search(const SearchParams& p, int metric, int dtype, int grid
                           int* blocks_per_sm);
 cudaError_t launch_search_lean(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
                                bool query_only, int* blocks_per_sm);
-cudaError_t launch_search_team(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
-                               bool query_only, int* blocks_per_sm);
+cudaError_t launch_search_lean_u8(const SearchParams& p, int metric, int grid, size_t smem, cudaStream_t st, bool query_only,
+                                  int* blocks_per_sm);
+cudaError_t launch_search_lean_u16(const SearchParams& p, int metric, int grid, size_t smem, cudaStream_t st, bool query_only,
+                                   int* blocks_per_sm);
 
 // ---- (metric, element type) -> distance functor.  f is called as f(OpTag<Op>{}) and returns cudaError_t.
 template <class Op>
@@ -130,13 +129,12 @@ template <> struct Specialise<OpL2> { static constexpr bool value = true; };
 template <> struct Specialise<OpDot> { static constexpr bool value = true; };
 template <> struct Specialise<OpCosine> { static constexpr bool value = true; };
 
-// ops the team kernel (search_team.cu) is instantiated for
-template <class Op>
-struct TeamOp {
-  static constexpr bool value = Specialise<Op>::value;
-};
-inline bool team_op_supported(int metric, int dtype) {
-  return dtype == DT_F32 && (metric == METRIC_L1 || metric == METRIC_L2 || metric == METRIC_DOT || metric == METRIC_COSINE);
+// (metric, element type) pairs the lean kernel (search_lean.cuh) is instantiated for
+inline bool lean_op_supported(int metric, int dtype) {
+  if (dtype == DT_F32) return metric == METRIC_L1 || metric == METRIC_L2 || metric == METRIC_DOT || metric == METRIC_COSINE;
+  if (dtype == DT_U8 || dtype == DT_U16)
+    return metric == METRIC_L1 || metric == METRIC_L2 || metric == METRIC_HAMMING || metric == METRIC_JACCARD;
+  return false;
 }
 
 template <class T, class F>

@@ -1,5 +1,4 @@
-// Pieces shared by the lean (search_lean.cu) and team (search_team.cu) query kernels: the reduction arithmetic of the
-// distance functors by type, the "still unexpanded" bit masks that stand for the reference's candidate heap C
+// Building blocks of the lean query kernel (search_lean.cuh): the reduction arithmetic of the distance functors by type, the "still unexpanded" bit masks that stand for the reference's candidate heap C
 // (/root/reference/src/hnsw.rs:940-1001), and shared-memory access through pinned 32-bit window addresses.
 #pragma once
 #include "common.cuh"

@@ -18,10 +18,11 @@
 //     (issuing one bulk copy per row costs ~8 instructions per row: the copy engine takes uniform operands);
 //   * two rows per lane group are reduced with one transposed reduction (3 shuffles for 2 rows, same sums);
 //   * the traversal counters are a template parameter: the production instantiation does not carry them.
+#pragma once
 #include <type_traits>
 
 #include "kernels.h"
-#include "team_common.cuh"
+#include "lean_common.cuh"
 
 namespace hb {
 
@@ -433,22 +434,18 @@ static cudaError_t launch_lean_for_op(const SearchParams& p, int grid, size_t sm
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_search_lean(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
-                               bool query_only, int* blocks_per_sm) {
-  return dispatch_op(metric, dtype, [&](auto tag) -> cudaError_t {
-    using Op = typename decltype(tag)::type;
+// one translation unit per element type instantiates the kernels (search_lean_f32.cu, search_lean_u8.cu, search_lean_u16.cu)
+template <class Op>
+static cudaError_t launch_lean_op(const SearchParams& p, int grid, size_t smem, cudaStream_t st, bool query_only, int* blocks_per_sm) {
 #ifdef HB_FAST_BUILD  // scripts/variants.sh: one instantiation, for A/B builds
-    if constexpr (std::is_same<Op, OpL2>::value) {
-      if (p.q_smem == 64) return launch_lean_for_op<Op, 64>(p, grid, smem, st, query_only, blocks_per_sm);
-    }
+  if constexpr (std::is_same<Op, OpL2>::value) {
+    if (p.q_smem == 64) return launch_lean_for_op<Op, 64>(p, grid, smem, st, query_only, blocks_per_sm);
+  }
 #else
-    if constexpr (TeamOp<Op>::value) {
-      if (p.q_smem == 64) return launch_lean_for_op<Op, 64>(p, grid, smem, st, query_only, blocks_per_sm);
-      if (p.q_smem == 128) return launch_lean_for_op<Op, 128>(p, grid, smem, st, query_only, blocks_per_sm);
-    }
+  if (p.q_smem == 64) return launch_lean_for_op<Op, 64>(p, grid, smem, st, query_only, blocks_per_sm);
+  if (p.q_smem == 128) return launch_lean_for_op<Op, 128>(p, grid, smem, st, query_only, blocks_per_sm);
 #endif
-    return cudaErrorInvalidValue;
-  });
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace hb

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../hnswlib-rs_b200/csrc"
 name=$1; flags=$2
 mkdir -p ../lib/variants
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v -DHB_FAST_BUILD $flags -c search_lean.cu -o ../lib/variants/search_lean_$name.o 2> ../lib/variants/$name.ptxas.log
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v -DHB_FAST_BUILD $flags -c search_lean_f32.cu -o ../lib/variants/search_lean_$name.o 2> ../lib/variants/$name.ptxas.log
 grep -A3 "OpL2ELi4ELi64ELb0" ../lib/variants/$name.ptxas.log | grep -E "Used|spill" | tr '\n' ' '; echo
-objs=$(ls ../lib/obj/*.o | grep -v search_lean.o)
+objs=$(ls ../lib/obj/*.o | grep -v search_lean_f32.o)
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/variants/libhnsw_b200_$name.so $objs ../lib/variants/search_lean_$name.o -lcudart_static -lpthread -ldl -lrt

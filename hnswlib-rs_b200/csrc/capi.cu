@@ -4,6 +4,7 @@
 #include <exception>
 #include <cstring>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -37,10 +38,15 @@ static int pass(Index* ix, int r) {
   return r;
 }
 
+// HB_H: exclusive access (anything that may change the index); HB_HS: shared access (searches, read-only queries)
 #define HB_H(h) \
   if (!(h)) return set_err("NULL handle"); \
   Index* ix = ((const AnyApi*)(h))->ix;    \
-  std::lock_guard<std::mutex> g__(ix->mu)
+  std::unique_lock<std::shared_mutex> g__(ix->mu)
+#define HB_HS(h) \
+  if (!(h)) return set_err("NULL handle"); \
+  Index* ix = ((const AnyApi*)(h))->ix;    \
+  std::shared_lock<std::shared_mutex> g__(ix->mu)
 
 static int metric_from_name(const uint8_t* name, size_t len) {
   std::string s((const char*)name, len);
@@ -91,7 +97,7 @@ static void insert_any(void* hv, size_t len, const void* data, size_t id) {
     set_err("insert: NULL argument");
     return;
   }
-  std::lock_guard<std::mutex> g(h->ix->mu);
+  std::unique_lock<std::shared_mutex> g(h->ix->mu);
   if (pass(h->ix, h->ix->set_dim((int)len))) return;
   uint64_t id64 = id;
   pass(h->ix, h->ix->insert_batch(data, 1, len, nullptr, &id64, nullptr));
@@ -103,7 +109,7 @@ static void parallel_insert_any(void* hv, size_t nb_vec, size_t vec_len, const v
     set_err("parallel_insert: NULL argument");
     return;
   }
-  std::lock_guard<std::mutex> g(h->ix->mu);
+  std::unique_lock<std::shared_mutex> g(h->ix->mu);
   if (pass(h->ix, h->ix->set_dim((int)vec_len))) return;
   std::vector<uint64_t> id64(ids, ids + nb_vec);
   pass(h->ix, h->ix->insert_batch(nullptr, nb_vec, vec_len, datas, id64.data(), nullptr));
@@ -115,7 +121,7 @@ static const Neighbourhood_api* search_any(const void* hv, size_t len, const voi
     set_err("search_neighbours: bad argument");
     return nullptr;
   }
-  std::lock_guard<std::mutex> g(h->ix->mu);
+  std::shared_lock<std::shared_mutex> g(h->ix->mu);
   Neighbour_api* nb = (Neighbour_api*)malloc(sizeof(Neighbour_api) * knbn);
   int32_t cnt = 0;
   if (pass(h->ix, h->ix->search_host(data, nullptr, 1, (int)len, knbn, ef_search, nullptr, (NeighbourOut*)nb, &cnt))) {
@@ -144,7 +150,7 @@ static const Vec_api_Neighbourhood_api* parallel_search_any(const void* hv, size
     set_err("parallel_search_neighbours: bad argument");
     return nullptr;
   }
-  std::lock_guard<std::mutex> g(h->ix->mu);
+  std::shared_lock<std::shared_mutex> g(h->ix->mu);
   VecApiBox* box = (VecApiBox*)malloc(sizeof(VecApiBox));
   box->hoods = (Neighbourhood_api*)malloc(sizeof(Neighbourhood_api) * (nb_vec ? nb_vec : 1));
   box->block = (Neighbour_api*)malloc(sizeof(Neighbour_api) * (nb_vec ? nb_vec * knbn : 1));
@@ -249,7 +255,7 @@ static int64_t file_dump_any(const void* hv, size_t namelen, const uint8_t* file
     set_err("file_dump: NULL argument");
     return -1;
   }
-  std::lock_guard<std::mutex> g(h->ix->mu);
+  std::shared_lock<std::shared_mutex> g(h->ix->mu);
   std::string used;
   // api.rs:76-78: the reference refuses to overwrite only while a dump is memory-mapped; nothing is mapped here
   if (pass(h->ix, h->ix->file_dump(".", std::string((const char*)filename, namelen), true, &used))) return -1;
@@ -479,7 +485,7 @@ int hnsw_b200_search_flat(const void* h, const void* queries, uint64_t nq, uint6
                           uint64_t ef_search, int filter_mode, const uint64_t* filter_ids, uint64_t nfilter,
                           hnsw_b200_filter_fn fn, void* ctx, uint64_t* out_ids, float* out_dist,
                           uint32_t* out_internal, int32_t* out_pid, int32_t* out_counts) {
-  HB_H(h);
+  HB_HS(h);
   if (nq == 0) return 0;
   if (!queries || !out_ids || !out_dist || !out_counts || knbn == 0) return set_err("bad argument");
   std::vector<uint32_t> bits;
@@ -494,7 +500,8 @@ int hnsw_b200_search_flat(const void* h, const void* queries, uint64_t nq, uint6
   auto run = [=](Index* rx, size_t first, size_t count) -> int {
     const NeighbourOut* tmp = nullptr;
     const int32_t* cnts = nullptr;
-    int r = rx->search_host_staged((const char*)queries + first * qrow, nullptr, count, (int)dim, knbn, ef_search, fb, &tmp, &cnts);
+    Index::CtxLease lease(rx);  // the answers stay in the context's pinned buffer until they are unpacked below
+    int r = rx->search_host_staged(lease.c, (const char*)queries + first * qrow, nullptr, count, (int)dim, knbn, ef_search, fb, &tmp, &cnts);
     if (r) return r;
     memcpy(out_counts + first, cnts, count * sizeof(int32_t));
     // the kernel fills the slots beyond a query's count with (~0, +inf, INVALID_ID): plain field copies
@@ -516,11 +523,19 @@ int hnsw_b200_search_flat(const void* h, const void* queries, uint64_t nq, uint6
 
 int hnsw_b200_search_device(const void* h, const void* d_queries, uint64_t nq, uint64_t knbn,
                             uint64_t ef_search, void* d_out, int32_t* d_counts, int sync, float* kernel_ms) {
-  HB_H(h);
+  HB_HS(h);
   return pass(ix, ix->search_device(d_queries, nq, knbn, ef_search, nullptr, (NeighbourOut*)d_out, d_counts, sync != 0,
                                     kernel_ms));
 }
 
+int hnsw_b200_join(void* h) {
+  HB_HS(h);
+  return pass(ix, ix->join());
+}
+int hnsw_b200_stream_wait_last(void* h, void* cuda_stream) {
+  HB_HS(h);
+  return pass(ix, ix->stream_wait_last((cudaStream_t)cuda_stream));
+}
 int hnsw_b200_set_stream(void* h, void* cuda_stream) {
   HB_H(h);
   return pass(ix, ix->set_stream((cudaStream_t)cuda_stream));
@@ -560,7 +575,7 @@ int hnsw_b200_export_vectors(const void* h, void* out) {
 int64_t hnsw_b200_flat_neighbours(const void* h, uint64_t origin_id, Neighbour_api* out, uint64_t cap) {
   if (!h) return set_err("NULL handle");
   Index* ix = ((const AnyApi*)h)->ix;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::shared_lock<std::shared_mutex> g(ix->mu);
   std::vector<uint64_t> off, nbo;
   std::vector<float> nbd;
   if (pass(ix, ix->flatten(off, nbo, nbd))) return -1;
@@ -578,7 +593,7 @@ int64_t hnsw_b200_flat_neighbours(const void* h, uint64_t origin_id, Neighbour_a
 int64_t hnsw_b200_flatten(const void* h, uint64_t* offsets, uint64_t* nb_origin, float* nb_dist) {
   if (!h) return set_err("NULL handle");
   Index* ix = ((const AnyApi*)h)->ix;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::shared_lock<std::shared_mutex> g(ix->mu);
   std::vector<uint64_t> off, nbo;
   std::vector<float> nbd;
   if (pass(ix, ix->flatten(off, nbo, nbd))) return -1;
@@ -591,7 +606,7 @@ int64_t hnsw_b200_flatten(const void* h, uint64_t* offsets, uint64_t* nb_origin,
 int64_t hnsw_b200_layer_edges(const void* h, int layer) {
   if (!h) return set_err("NULL handle");
   Index* ix = ((const AnyApi*)h)->ix;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::shared_lock<std::shared_mutex> g(ix->mu);
   int64_t total = 0;
   if (pass(ix, ix->export_layer(layer, nullptr, nullptr, nullptr, &total))) return -1;
   return total;

@@ -27,13 +27,20 @@ static int ilog2(size_t p) {
   return r;
 }
 
+// searches run concurrently: the message of the last failure is guarded (the C ABI copies it into a thread-local string)
 int Index::fail(const std::string& m) const {
+  std::lock_guard<std::mutex> lk(err_mu_);
   err_ = m;
   return -1;
 }
 int Index::cuda_fail(cudaError_t e, const char* what) const {
+  std::lock_guard<std::mutex> lk(err_mu_);
   err_ = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
   return -2;
+}
+std::string Index::err() const {
+  std::lock_guard<std::mutex> lk(err_mu_);
+  return err_;
 }
 
 Index::Index(int M_, size_t max_elements_, int max_layer_, int ef_c_, int metric_, int dtype_, int device_)
@@ -52,10 +59,20 @@ Index::Index(int M_, size_t max_elements_, int max_layer_, int ef_c_, int metric
     err_ = "device index out of range";
     return;
   }
-  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaEventCreate(&ev0_)) != cudaSuccess || (e = cudaEventCreate(&ev1_)) != cudaSuccess) {
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)) != cudaSuccess) {
     err_ = std::string("CUDA init failed: ") + cudaGetErrorString(e);
     return;
+  }
+  for (SearchCtx& c : ctx_) {
+    if ((e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreate(&c.ev0)) != cudaSuccess || (e = cudaEventCreate(&c.ev1)) != cudaSuccess ||
+        (e = cudaMalloc(&c.d_counter, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&c.d_status, sizeof(int))) != cudaSuccess ||
+        (e = cudaMemset(c.d_status, 0, sizeof(int))) != cudaSuccess) {
+      err_ = std::string("CUDA init failed: ") + cudaGetErrorString(e);
+      return;
+    }
   }
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
@@ -84,12 +101,20 @@ Index::~Index() {
   if (stream_) cudaStreamSynchronize(stream_);
   cudaFree(d_vec_.p); cudaFree(d_adj0_.p); cudaFree(d_adjU_.p); cudaFree(d_upoff_.p); cudaFree(d_adj0d_.p);
   cudaFree(d_adjUd_.p); cudaFree(d_level_.p); cudaFree(d_plevel_.p); cudaFree(d_origin_.p); cudaFree(d_locks_.p);
-  cudaFree(vis_.tab); cudaFree(vis_.epoch); cudaFree(svis_.tab); cudaFree(svis_.epoch); cudaFree(d_counter_); cudaFree(d_status_); cudaFree(d_stats_);
-  cudaFree(d_q_); cudaFree(d_out_); cudaFree(d_cnt_); cudaFree(d_fbits_); cudaFree(d_mask_); cudaFree(d_cbuf_);
+  cudaFree(vis_.tab); cudaFree(vis_.epoch); cudaFree(d_counter_); cudaFree(d_status_); cudaFree(d_stats_); cudaFree(d_mask_);
   if (h_pin_) cudaFreeHost(h_pin_);
-  if (h_res_) cudaFreeHost(h_res_);
-  if (ev0_) cudaEventDestroy(ev0_);
-  if (ev1_) cudaEventDestroy(ev1_);
+  for (SearchCtx& c : ctx_) {
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    cudaFree(c.vis.tab); cudaFree(c.vis.epoch); cudaFree(c.fvis.tab); cudaFree(c.fvis.epoch); cudaFree(c.d_counter); cudaFree(c.d_status);
+    cudaFree(c.d_q); cudaFree(c.d_out); cudaFree(c.d_cnt); cudaFree(c.d_fbits); cudaFree(c.d_cbuf);
+    if (c.h_pin) cudaFreeHost(c.h_pin);
+    if (c.h_res) cudaFreeHost(c.h_res);
+    if (c.fork) cudaEventDestroy(c.fork);
+    if (c.join) cudaEventDestroy(c.join);
+    if (c.ev0) cudaEventDestroy(c.ev0);
+    if (c.ev1) cudaEventDestroy(c.ev1);
+    if (c.stream) cudaStreamDestroy(c.stream);
+  }
   if (own_stream_) cudaStreamDestroy(own_stream_);
 }
 
@@ -150,32 +175,32 @@ int Index::ensure_upper(size_t need) {
 // A pool is laid out as [slots][cap] for the (slots, cap) it was last sized for.  Insert and filtered search share one
 // pool (large tables); unfiltered searches own another, so that their small L2-resident tables are not inflated by
 // the insert path's (4x larger: ef_construction instead of ef).
-int Index::ensure_visited(VisitedPool& v, size_t slots, size_t cap_entries) {
+int Index::ensure_visited(VisitedPool& v, size_t slots, size_t cap_entries, cudaStream_t st) {
   if (slots <= v.slots && cap_entries <= v.cap) return 0;
   size_t ns = std::max(slots, v.slots), nc = std::max(cap_entries, v.cap);
   if (ns * nc * sizeof(uint32_t) > ((size_t)8 << 30)) {  // do not carry a huge shape over (filtered searches use few, big tables)
     ns = slots;
     nc = cap_entries;
   }
-  HB_CUDA(cudaStreamSynchronize(stream_));
+  HB_CUDA(cudaStreamSynchronize(st));
   cudaFree(v.tab);
   cudaFree(v.epoch);
   v.tab = v.epoch = nullptr;
   v.slots = v.cap = 0;
   HB_CUDA(cudaMalloc(&v.tab, ns * nc * sizeof(uint32_t)));
   HB_CUDA(cudaMalloc(&v.epoch, ns * sizeof(uint32_t)));
-  HB_CUDA(cudaMemsetAsync(v.tab, 0, ns * nc * sizeof(uint32_t), stream_));
+  HB_CUDA(cudaMemsetAsync(v.tab, 0, ns * nc * sizeof(uint32_t), st));
   // epoch = max forces a table clear on first use whatever id_bits is (Visited::begin)
-  HB_CUDA(cudaMemsetAsync(v.epoch, 0xFF, ns * sizeof(uint32_t), stream_));
+  HB_CUDA(cudaMemsetAsync(v.epoch, 0xFF, ns * sizeof(uint32_t), st));
   v.slots = ns;
   v.cap = nc;
   return 0;
 }
 
-int Index::fill_visited_cfg(VisitedPool& v, VisitedCfg& c) {
+int Index::fill_visited_cfg(VisitedPool& v, VisitedCfg& c, cudaStream_t st) {
   const int id_bits = std::max(1, ilog2(std::max<size_t>(cap_, 2)));
   if (id_bits != v.id_bits) {  // entries are (epoch << id_bits) | id: a new split invalidates every table
-    HB_CUDA(cudaMemsetAsync(v.epoch, 0xFF, v.slots * sizeof(uint32_t), stream_));
+    HB_CUDA(cudaMemsetAsync(v.epoch, 0xFF, v.slots * sizeof(uint32_t), st));
     v.id_bits = id_bits;
   }
   c.tables = v.tab;
@@ -186,9 +211,9 @@ int Index::fill_visited_cfg(VisitedPool& v, VisitedCfg& c) {
   return 0;
 }
 
-int Index::ensure_scratch(void** p, size_t* cur, size_t need) {
+int Index::ensure_scratch(void** p, size_t* cur, size_t need, cudaStream_t st) {
   if (need <= *cur) return 0;
-  HB_CUDA(cudaStreamSynchronize(stream_));
+  HB_CUDA(cudaStreamSynchronize(st));
   cudaFree(*p);
   *p = nullptr;
   *cur = 0;
@@ -305,8 +330,8 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
   size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)2 * (ef_c + 16) * p.g.deg0));
   for (int attempt = 0;; ++attempt) {
     int r;
-    if ((r = ensure_visited(vis_, (size_t)grid * wpb, vcap))) return r;
-    if ((r = fill_visited_cfg(vis_, p.vis))) return r;
+    if ((r = ensure_visited(vis_, (size_t)grid * wpb, vcap, stream_))) return r;
+    if ((r = fill_visited_cfg(vis_, p.vis, stream_))) return r;
     HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
     HB_CUDA(launch_insert_search(p, metric, dtype, grid, smem, stream_, false, nullptr));
     int status = 0;
@@ -396,7 +421,7 @@ int Index::insert_batch(const void* vecs, size_t n_new, size_t stride, const voi
   HB_CUDA(cudaMemcpyAsync(d_plevel_.p + first, h_plevel.data() + first, n_new, cudaMemcpyHostToDevice, stream_));
   HB_CUDA(cudaMemcpyAsync(d_origin_.p + first, h_origin.data() + first, n_new * 8, cudaMemcpyHostToDevice, stream_));
   HB_CUDA(cudaMemcpyAsync(d_upoff_.p + first, h_upoff.data() + first, n_new * 4, cudaMemcpyHostToDevice, stream_));
-  if ((r = ensure_scratch(&d_mask_, &d_mask_bytes_, n_new * 2))) return r;
+  if ((r = ensure_scratch(&d_mask_, &d_mask_bytes_, n_new * 2, stream_))) return r;
   HB_CUDA(cudaMemcpyAsync(d_mask_, masks.data(), n_new * 2, cudaMemcpyHostToDevice, stream_));
   n = first + n_new;  // stored; points become reachable as their batch links them
   // ---- schedule batches
@@ -547,15 +572,79 @@ int Index::import_graph(const void* vecs, size_t n_new, int d, const uint64_t* o
 
 // ------------------------------------------------------------------------------------------------
 // search
+int Index::acquire_ctx() {
+  std::unique_lock<std::mutex> lk(ctx_mu_);
+  for (;;) {
+    for (int i = 0; i < NCTX; ++i)
+      if (!ctx_[i].busy) {
+        ctx_[i].busy = true;
+        return i;
+      }
+    ctx_cv_.wait(lk);
+  }
+}
+void Index::release_ctx(int c) {
+  {
+    std::lock_guard<std::mutex> lk(ctx_mu_);
+    ctx_[c].busy = false;
+  }
+  ctx_cv_.notify_one();
+}
+
+// Device-resident search.  sync: runs on a leased context, returns when the answers are there.  Asynchronous: the launch
+// is forked from the handle's stream (it waits for everything enqueued there so far) onto the next of two alternating
+// context streams, so that two consecutive launches overlap.  The handle's stream does NOT wait for it: join() (or
+// check_status, set_stream, any synchronous call's own synchronisation) makes it do so; stream_wait_last() makes any
+// stream wait for the most recent launch alone.
 int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_arg, const uint32_t* d_filter_bits,
                          NeighbourOut* d_out, int32_t* d_counts, bool sync, float* kernel_ms) {
   if (nq == 0) return 0;
+  HB_CUDA(cudaSetDevice(device));
+  if (sync) {
+    CtxLease lease(this);
+    SearchCtx& c = ctx_[lease.c];
+    HB_CUDA(cudaEventRecord(c.fork, stream_));
+    HB_CUDA(cudaStreamWaitEvent(c.stream, c.fork, 0));
+    return search_on_ctx(c, d_queries, nq, k, ef_arg, d_filter_bits, d_out, d_counts, true, kernel_ms);
+  }
+  int ci;
+  {
+    std::lock_guard<std::mutex> lk(ctx_mu_);
+    ci = NCTX + (int)(ctx_rr_++ % NASYNC);  // two contexts alternate: the tail of one launch overlaps the bulk of the next
+  }
+  SearchCtx& c = ctx_[ci];
+  HB_CUDA(cudaEventRecord(c.fork, stream_));
+  HB_CUDA(cudaStreamWaitEvent(c.stream, c.fork, 0));
+  int r = search_on_ctx(c, d_queries, nq, k, ef_arg, d_filter_bits, d_out, d_counts, false, nullptr);
+  if (r) return r;
+  HB_CUDA(cudaEventRecord(c.join, c.stream));
+  last_async_ = ci;
+  return 0;
+}
+
+int Index::join() {
+  HB_CUDA(cudaSetDevice(device));
+  for (int i = NCTX; i < NCTX + NASYNC; ++i) {
+    HB_CUDA(cudaEventRecord(ctx_[i].join, ctx_[i].stream));
+    HB_CUDA(cudaStreamWaitEvent(stream_, ctx_[i].join, 0));
+  }
+  return 0;
+}
+
+int Index::stream_wait_last(cudaStream_t s) {
+  HB_CUDA(cudaSetDevice(device));
+  if (last_async_ >= 0) HB_CUDA(cudaStreamWaitEvent(s ? s : stream_, ctx_[last_async_].join, 0));
+  return 0;
+}
+
+int Index::search_on_ctx(SearchCtx& c, const void* d_queries, size_t nq, size_t k, size_t ef_arg, const uint32_t* d_filter_bits,
+                         NeighbourOut* d_out, int32_t* d_counts, bool sync, float* kernel_ms) {
   if (k == 0) return fail("knbn must be positive");
   if (poisoned_) return fail(poison_msg_);
-  HB_CUDA(cudaSetDevice(device));
+  cudaStream_t st = c.stream;
   if (dim == 0) {  // empty index: every answer is empty (hnsw.rs:1498-1503)
-    HB_CUDA(cudaMemsetAsync(d_counts, 0, nq * sizeof(int32_t), stream_));
-    if (sync) HB_CUDA(cudaStreamSynchronize(stream_));
+    HB_CUDA(cudaMemsetAsync(d_counts, 0, nq * sizeof(int32_t), st));
+    if (sync) HB_CUDA(cudaStreamSynchronize(st));
     return 0;
   }
   SearchParams p;
@@ -570,12 +659,12 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
   while (layer0 < MAX_LAYERS - 1 && layer_count[layer0] == 0) layer0++;
   if (n == 0) layer0 = 0;
   p.layer0 = layer0;
-  p.work_counter = d_counter_;
+  p.work_counter = c.d_counter;
   p.out_nb = d_out;
   p.out_count = d_counts;
   p.filter_bits = d_filter_bits;
   p.stats = stats_on_ ? d_stats_ : nullptr;
-  p.status = d_status_;
+  p.status = c.d_status;
   const bool filtered = d_filter_bits != nullptr;
   // kernel choice: lean (search_lean.cuh) whenever it applies, else the generic warp kernel (search.cu / filter.cu)
   const bool lean = !filtered && kernel_pref_ == 0 && entry != INVALID_ID && lean_eligible(p.g.d4, p.ef) && lean_op_supported(metric, dtype);
@@ -590,14 +679,15 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
   p.ccap = 0;
   int bps = 0;
   {
+    std::lock_guard<std::mutex> lk(occ_mu_);
     const auto key = std::make_tuple(lean ? 3 : (int)filtered, lean ? p.q_smem : p.q_kind, p.g.d4, smem);
     auto it = occ_cache_.find(key);
     if (it != occ_cache_.end()) {
       bps = it->second;
     } else {
-      if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, 0, smem, stream_, true, &bps));
-      else if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, 0, smem, stream_, true, &bps));
-      else HB_CUDA(launch_search(p, metric, dtype, 0, smem, stream_, true, &bps));
+      if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, 0, smem, st, true, &bps));
+      else if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, 0, smem, st, true, &bps));
+      else HB_CUDA(launch_search(p, metric, dtype, 0, smem, st, true, &bps));
       occ_cache_[key] = bps;
     }
   }
@@ -606,10 +696,10 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
   int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (nq + per_cta - 1) / per_cta);
   const int deg = layer0 == 0 ? 2 * M : M;
   // visited-table capacity per query slot: a search inserts ~ (ef + a few) * (fresh neighbours per expansion) ids.  An
-  // overflow is detected in the kernel and the batch re-run with doubled tables.  Searches have their own pool: the
-  // insert path's tables are 4x larger (ef_construction) and would push the search's out of L2.
+  // overflow is detected in the kernel and the batch re-run with doubled tables.  (The insert path has its own pool:
+  // its tables are 4x larger, ef_construction instead of ef, and would push the search's out of L2.)
   size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)2 * (p.ef + 16) * deg));
-  VisitedPool& pool = filtered ? vis_ : svis_;
+  VisitedPool& pool = filtered ? c.fvis : c.vis;
   for (int attempt = 0;; ++attempt) {
     int r;
     if (filtered) {
@@ -619,32 +709,32 @@ int Index::search_device(const void* d_queries, size_t nq, size_t k, size_t ef_a
       const size_t max_slots = std::max<size_t>(wpb, ((size_t)6 << 30) / per_slot);
       grid = (int)std::max<size_t>(1, std::min<size_t>(grid, max_slots / wpb));
     }
-    if ((r = ensure_visited(pool, (size_t)grid * per_cta, vcap))) return r;
-    if ((r = fill_visited_cfg(pool, p.vis))) return r;
+    if ((r = ensure_visited(pool, (size_t)grid * per_cta, vcap, st))) return r;
+    if ((r = fill_visited_cfg(pool, p.vis, st))) return r;
     if (filtered) {
-      if ((r = ensure_scratch(&d_cbuf_, &d_cbuf_bytes_, (size_t)grid * wpb * pool.cap * 8))) return r;
-      p.cbuf = (uint64_t*)d_cbuf_;
+      if ((r = ensure_scratch(&c.d_cbuf, &c.d_cbuf_bytes, (size_t)grid * wpb * pool.cap * 8, st))) return r;
+      p.cbuf = (uint64_t*)c.d_cbuf;
       p.ccap = (uint32_t)pool.cap;
     }
-    HB_CUDA(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), stream_));
-    HB_CUDA(cudaEventRecord(ev0_, stream_));
-    if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, grid, smem, stream_, false, nullptr));
-    else if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, grid, smem, stream_, false, nullptr));
-    else HB_CUDA(launch_search(p, metric, dtype, grid, smem, stream_, false, nullptr));
-    HB_CUDA(cudaEventRecord(ev1_, stream_));
+    HB_CUDA(cudaMemsetAsync(c.d_counter, 0, sizeof(unsigned int), st));
+    HB_CUDA(cudaEventRecord(c.ev0, st));
+    if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, grid, smem, st, false, nullptr));
+    else if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, grid, smem, st, false, nullptr));
+    else HB_CUDA(launch_search(p, metric, dtype, grid, smem, st, false, nullptr));
+    HB_CUDA(cudaEventRecord(c.ev1, st));
     if (!sync) break;
     int status = 0;
-    HB_CUDA(cudaMemcpyAsync(&status, d_status_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    HB_CUDA(cudaStreamSynchronize(stream_));
+    HB_CUDA(cudaMemcpyAsync(&status, c.d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaStreamSynchronize(st));
     if (status == 0) {
-      if (kernel_ms) HB_CUDA(cudaEventElapsedTime(kernel_ms, ev0_, ev1_));
+      if (kernel_ms) HB_CUDA(cudaEventElapsedTime(kernel_ms, c.ev0, c.ev1));
       break;
     }
     if (attempt >= 24) return fail("visited table overflow persists");
-    HB_CUDA(cudaMemsetAsync(d_status_, 0, sizeof(int), stream_));
+    HB_CUDA(cudaMemsetAsync(c.d_status, 0, sizeof(int), st));
     vcap = pool.cap * 2;
   }
-  stat_queries_ += stats_on_ ? nq : 0;
+  if (stats_on_) stat_queries_ += nq;
   return 0;
 }
 
@@ -666,8 +756,10 @@ static const void* device_view_of_host(const void* p) {
 // buffer: no cudaMemcpy before or after the launch, one synchronisation.  Pageable queries and row pointers are
 // gathered into the index's own pinned staging buffer first (the only host-side copy), which the kernel then reads
 // the same way.  zero_copy_ = false (env HNSW_B200_ZERO_COPY=0) restores explicit H2D / D2H copies.
-int Index::search_host_staged(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
+int Index::search_host_staged(int ci, const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
                               const uint32_t* filter_bits_host, const NeighbourOut** out, const int32_t** counts) {
+  SearchCtx& c = ctx_[ci];
+  cudaStream_t st = c.stream;
   *out = nullptr;
   *counts = nullptr;
   if (nq == 0) return 0;
@@ -675,15 +767,15 @@ int Index::search_host_staged(const void* queries, const void* const* rows, size
   if (dim != 0 && d != dim) return fail("query length differs from the index dimension");
   int r;
   const size_t out_bytes = nq * k * sizeof(NeighbourOut), cnt_bytes = nq * sizeof(int32_t);
-  if (h_res_bytes_ < out_bytes + cnt_bytes + 16) {
-    if (h_res_) cudaFreeHost(h_res_);
-    h_res_ = nullptr;
-    h_res_bytes_ = 0;
-    HB_CUDA(cudaHostAlloc(&h_res_, out_bytes + cnt_bytes + 16, cudaHostAllocMapped | cudaHostAllocPortable));
-    h_res_bytes_ = out_bytes + cnt_bytes + 16;
+  if (c.h_res_bytes < out_bytes + cnt_bytes + 16) {
+    if (c.h_res) cudaFreeHost(c.h_res);
+    c.h_res = nullptr;
+    c.h_res_bytes = 0;
+    HB_CUDA(cudaHostAlloc(&c.h_res, out_bytes + cnt_bytes + 16, cudaHostAllocMapped | cudaHostAllocPortable));
+    c.h_res_bytes = out_bytes + cnt_bytes + 16;
   }
-  NeighbourOut* hout = (NeighbourOut*)h_res_;
-  int32_t* hcnt = (int32_t*)((char*)h_res_ + out_bytes);
+  NeighbourOut* hout = (NeighbourOut*)c.h_res;
+  int32_t* hcnt = (int32_t*)((char*)c.h_res + out_bytes);
   int32_t* hstatus = hcnt + nq;
   *out = hout;
   *counts = hcnt;
@@ -698,14 +790,14 @@ int Index::search_host_staged(const void* queries, const void* const* rows, size
   if (rows || !(zero_copy_ && device_view_of_host(queries))) {
     // gather into pinned staging (rows: one pointer per query, libext.rs parallel_search_neighbours_<ty>)
     if (rows || !device_view_of_host(queries)) {
-      if (h_pin_bytes_ < qbytes) {
-        if (h_pin_) cudaFreeHost(h_pin_);
-        h_pin_ = nullptr;
-        h_pin_bytes_ = 0;
-        HB_CUDA(cudaHostAlloc(&h_pin_, qbytes, cudaHostAllocMapped | cudaHostAllocPortable));
-        h_pin_bytes_ = qbytes;
+      if (c.h_pin_bytes < qbytes) {
+        if (c.h_pin) cudaFreeHost(c.h_pin);
+        c.h_pin = nullptr;
+        c.h_pin_bytes = 0;
+        HB_CUDA(cudaHostAlloc(&c.h_pin, qbytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        c.h_pin_bytes = qbytes;
       }
-      unsigned char* st = (unsigned char*)h_pin_;
+      unsigned char* st = (unsigned char*)c.h_pin;
       if (rows)
         for (size_t i = 0; i < nq; ++i) memcpy(st + i * (size_t)dim * es, rows[i], (size_t)dim * es);
       else
@@ -715,54 +807,55 @@ int Index::search_host_staged(const void* queries, const void* const* rows, size
   }
   if (zero_copy_) d_queries = device_view_of_host(host_src);
   if (!d_queries) {
-    if ((r = ensure_scratch(&d_q_, &d_q_bytes_, qbytes))) return r;
-    HB_CUDA(cudaMemcpyAsync(d_q_, host_src, qbytes, cudaMemcpyHostToDevice, stream_));
-    d_queries = d_q_;
+    if ((r = ensure_scratch(&c.d_q, &c.d_q_bytes, qbytes, st))) return r;
+    HB_CUDA(cudaMemcpyAsync(c.d_q, host_src, qbytes, cudaMemcpyHostToDevice, st));
+    d_queries = c.d_q;
   }
   NeighbourOut* k_out = nullptr;  // where the kernel writes
   int32_t* k_cnt = nullptr;
-  const void* dv = zero_copy_ ? device_view_of_host(h_res_) : nullptr;
+  const void* dv = zero_copy_ ? device_view_of_host(c.h_res) : nullptr;
   if (dv) {
     k_out = (NeighbourOut*)dv;
     k_cnt = (int32_t*)((char*)dv + out_bytes);
   } else {
-    if ((r = ensure_scratch(&d_out_, &d_out_bytes_, out_bytes))) return r;
-    if ((r = ensure_scratch(&d_cnt_, &d_cnt_bytes_, cnt_bytes))) return r;
-    k_out = (NeighbourOut*)d_out_;
-    k_cnt = (int32_t*)d_cnt_;
+    if ((r = ensure_scratch(&c.d_out, &c.d_out_bytes, out_bytes, st))) return r;
+    if ((r = ensure_scratch(&c.d_cnt, &c.d_cnt_bytes, cnt_bytes, st))) return r;
+    k_out = (NeighbourOut*)c.d_out;
+    k_cnt = (int32_t*)c.d_cnt;
   }
   const uint32_t* dfb = nullptr;
   if (filter_bits_host) {
     const size_t fb = ((n + 31) / 32) * 4;
-    if ((r = ensure_scratch(&d_fbits_, &d_fbits_bytes_, fb))) return r;
-    HB_CUDA(cudaMemcpyAsync(d_fbits_, filter_bits_host, fb, cudaMemcpyHostToDevice, stream_));
-    dfb = (const uint32_t*)d_fbits_;
+    if ((r = ensure_scratch(&c.d_fbits, &c.d_fbits_bytes, fb, st))) return r;
+    HB_CUDA(cudaMemcpyAsync(c.d_fbits, filter_bits_host, fb, cudaMemcpyHostToDevice, st));
+    dfb = (const uint32_t*)c.d_fbits;
   }
   // one enqueue (copies if any, kernel, status), one synchronisation; the slow path (a visited table overflowed: grow
   // and re-run) is taken only when the status says so
   for (int pass = 0; pass < 2; ++pass) {
-    if ((r = search_device(d_queries, nq, k, ef, dfb, k_out, k_cnt, pass == 1, nullptr))) return r;
+    if ((r = search_on_ctx(c, d_queries, nq, k, ef, dfb, k_out, k_cnt, pass == 1, nullptr))) return r;
     if (!dv) {
-      HB_CUDA(cudaMemcpyAsync(hout, d_out_, out_bytes, cudaMemcpyDeviceToHost, stream_));
-      HB_CUDA(cudaMemcpyAsync(hcnt, d_cnt_, cnt_bytes, cudaMemcpyDeviceToHost, stream_));
+      HB_CUDA(cudaMemcpyAsync(hout, c.d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+      HB_CUDA(cudaMemcpyAsync(hcnt, c.d_cnt, cnt_bytes, cudaMemcpyDeviceToHost, st));
     }
-    HB_CUDA(cudaMemcpyAsync(hstatus, d_status_, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-    HB_CUDA(cudaStreamSynchronize(stream_));
+    HB_CUDA(cudaMemcpyAsync(hstatus, c.d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaStreamSynchronize(st));
     if (*hstatus == 0) break;
     if (pass == 1) return fail("visited table overflow persists");
-    HB_CUDA(cudaMemsetAsync(d_status_, 0, sizeof(int), stream_));
+    HB_CUDA(cudaMemsetAsync(c.d_status, 0, sizeof(int), st));
   }
   return 0;
 }
 
 int Index::search_host(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
                        const uint32_t* filter_bits_host, NeighbourOut* out, int32_t* counts) {
+  CtxLease lease(this);
   const NeighbourOut* so;
   const int32_t* sc;
-  int r = search_host_staged(queries, rows, nq, d, k, ef, filter_bits_host, &so, &sc);
+  int r = search_host_staged(lease.c, queries, rows, nq, d, k, ef, filter_bits_host, &so, &sc);
   if (r || nq == 0) return r;
   memcpy(counts, sc, nq * sizeof(int32_t));
-  if (dim != 0) memcpy(out, so, nq * k * sizeof(NeighbourOut));
+  memcpy(out, so, nq * k * sizeof(NeighbourOut));
   return 0;
 }
 
@@ -871,6 +964,7 @@ int Index::export_vectors(void* out) const {
 
 int Index::set_stream(cudaStream_t s) {
   HB_CUDA(cudaSetDevice(device));
+  for (SearchCtx& c : ctx_) HB_CUDA(cudaStreamSynchronize(c.stream));
   HB_CUDA(cudaStreamSynchronize(stream_));
   stream_ = s ? s : own_stream_;
   return 0;
@@ -878,11 +972,16 @@ int Index::set_stream(cudaStream_t s) {
 
 int Index::check_status() {
   HB_CUDA(cudaSetDevice(device));
-  int status = 0;
-  HB_CUDA(cudaMemcpyAsync(&status, d_status_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
   HB_CUDA(cudaStreamSynchronize(stream_));
-  if (status) HB_CUDA(cudaMemset(d_status_, 0, sizeof(int)));
-  return status ? 1 : 0;
+  int any = 0;
+  for (SearchCtx& c : ctx_) {
+    int status = 0;
+    HB_CUDA(cudaMemcpyAsync(&status, c.d_status, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    HB_CUDA(cudaStreamSynchronize(c.stream));
+    if (status) HB_CUDA(cudaMemset(c.d_status, 0, sizeof(int)));
+    any |= status;
+  }
+  return any ? 1 : 0;
 }
 
 int Index::enable_stats(bool on) {

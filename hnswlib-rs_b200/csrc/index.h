@@ -7,10 +7,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <functional>
 #include <map>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
+#include <shared_mutex>
 #include <tuple>
 #include <string>
 #include <vector>
@@ -95,8 +98,8 @@ class Index {
   // host queries (flat or row pointers); results to host NeighbourOut[nq][k] + counts
   int search_host(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
                   const uint32_t* filter_bits_host, NeighbourOut* out, int32_t* counts);
-  // same, answers left in the index's pinned staging buffers (valid until the next call on this index)
-  int search_host_staged(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
+  // same on context c (a CtxLease), answers left in the context's pinned buffer (valid until the lease ends)
+  int search_host_staged(int c, const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
                          const uint32_t* filter_bits_host, const NeighbourOut** out, const int32_t** counts);
   int search_device(const void* d_queries, size_t nq, size_t k, size_t ef, const uint32_t* d_filter_bits,
                     NeighbourOut* d_out, int32_t* d_counts, bool sync, float* kernel_ms);
@@ -135,30 +138,65 @@ class Index {
   int nccl_allgather(const void* d_send, void* d_recv, size_t bytes_per_rank, cudaStream_t s);
   void nccl_destroy();
 
-  int dist_batch(const void* queries, size_t nq, int d, const uint32_t* cand, size_t m, float* out);
-  int bruteforce(const void* queries, size_t nq, int d, size_t k, uint32_t* out_ids, float* out_dist);
-
-  const std::string& err() const { return err_; }
-  GraphView view() const;
-  cudaStream_t stream() const { return stream_; }
-  int set_stream(cudaStream_t s);   // run on a caller-owned stream (e.g. torch's current stream); nullptr = own stream
-  int check_status();               // synchronise; 0 ok, 1 = a visited table overflowed since the last check
-  mutable std::mutex mu;  // the C ABI allows calls from many host threads (hnsw.rs:830-833)
-
- private:
-  int fail(const std::string& m) const;
-  int cuda_fail(cudaError_t e, const char* what) const;
-  int ensure_points(size_t need);
-  int ensure_upper(size_t need_lists);
+  // ---- search contexts.  Everything a running search owns besides the (read-only) graph: stream, work counter,
+  // status flag, visited tables, staging buffers.  Up to NCTX searches are in flight at once: calls from several host
+  // threads (the reference serves concurrent searches, hnsw.rs:830-833) and consecutive asynchronous device-resident
+  // launches, whose last queries then overlap the next launch's first (a launch ends with a few long searches that
+  // leave most SMs idle).
   struct VisitedPool {
     uint32_t* tab = nullptr;
     uint32_t* epoch = nullptr;
     size_t slots = 0, cap = 0;
     int id_bits = 0;
   };
-  int ensure_visited(VisitedPool& v, size_t slots, size_t cap_entries);
-  int fill_visited_cfg(VisitedPool& v, VisitedCfg& c);
-  int ensure_scratch(void** p, size_t* cur, size_t need);
+  struct SearchCtx {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, ev0 = nullptr, ev1 = nullptr;
+    unsigned int* d_counter = nullptr;
+    int* d_status = nullptr;
+    VisitedPool vis, fvis;  // unfiltered / filtered searches
+    void *d_q = nullptr, *d_out = nullptr, *d_cnt = nullptr, *d_fbits = nullptr, *d_cbuf = nullptr;
+    size_t d_q_bytes = 0, d_out_bytes = 0, d_cnt_bytes = 0, d_fbits_bytes = 0, d_cbuf_bytes = 0;
+    void *h_pin = nullptr, *h_res = nullptr;  // pinned, mapped: query staging / answers
+    size_t h_pin_bytes = 0, h_res_bytes = 0;
+    bool busy = false;
+  };
+  static constexpr int NCTX = 4;    // leased by synchronous calls (host threads)
+  static constexpr int NASYNC = 2;  // alternated by asynchronous device-resident launches (never leased)
+  int acquire_ctx();            // blocks until a context is free
+  void release_ctx(int c);
+  SearchCtx& ctx(int c) { return ctx_[c]; }
+  struct CtxLease {             // RAII: answers returned by search_host_staged live in the context until release
+    Index* ix;
+    int c;
+    explicit CtxLease(Index* i) : ix(i), c(i->acquire_ctx()) {}
+    ~CtxLease() { ix->release_ctx(c); }
+    CtxLease(const CtxLease&) = delete;
+    CtxLease& operator=(const CtxLease&) = delete;
+  };
+
+  int dist_batch(const void* queries, size_t nq, int d, const uint32_t* cand, size_t m, float* out);
+  int bruteforce(const void* queries, size_t nq, int d, size_t k, uint32_t* out_ids, float* out_dist);
+
+  std::string err() const;
+  GraphView view() const;
+  cudaStream_t stream() const { return stream_; }
+  int join();                           // the handle's stream waits for every asynchronous launch enqueued so far
+  int stream_wait_last(cudaStream_t s);  // `s` waits for the most recent asynchronous launch
+  int set_stream(cudaStream_t s);   // run on a caller-owned stream (e.g. torch's current stream); nullptr = own stream
+  int check_status();               // synchronise; 0 ok, 1 = a visited table overflowed since the last check
+  // the C ABI allows calls from many host threads (hnsw.rs:830-833): searches share the graph, anything that changes it
+  // (insert, import, load, replicate) holds it exclusively
+  mutable std::shared_mutex mu;
+
+ private:
+  int fail(const std::string& m) const;
+  int cuda_fail(cudaError_t e, const char* what) const;
+  int ensure_points(size_t need);
+  int ensure_upper(size_t need_lists);
+  int ensure_visited(VisitedPool& v, size_t slots, size_t cap_entries, cudaStream_t st);
+  int fill_visited_cfg(VisitedPool& v, VisitedCfg& c, cudaStream_t st);
+  int ensure_scratch(void** p, size_t* cur, size_t need, cudaStream_t st);
   int grow_plevel(uint32_t id, int new_plevel);
   int run_insert_range(size_t first, size_t count, const std::vector<uint16_t>& masks, size_t mask_off);
   int check_insert_fit();
@@ -183,8 +221,8 @@ class Index {
   bool poisoned_ = false;  // a CUDA failure interrupted an insert: the graph may hold half-written links
   std::string poison_msg_;
   mutable std::string err_;
+  mutable std::mutex err_mu_;
   cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
-  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   int sm_count_ = 0;
 
   size_t cap_ = 0, cap_ul_ = 0;
@@ -195,34 +233,29 @@ class Index {
   DevArray<uint64_t> d_origin_;
   DevArray<int> d_locks_;
 
-  // visited tables: vis_ serves insert and filtered search, svis_ the unfiltered searches
-  VisitedPool vis_, svis_;
+  VisitedPool vis_;  // visited tables of the insert kernel (searches: SearchCtx)
+  SearchCtx ctx_[NCTX + NASYNC];
+  int search_on_ctx(SearchCtx& c, const void* d_queries, size_t nq, size_t k, size_t ef_arg, const uint32_t* d_filter_bits,
+                    NeighbourOut* d_out, int32_t* d_counts, bool sync, float* kernel_ms);
+  std::mutex ctx_mu_;
+  std::condition_variable ctx_cv_;
+  int last_async_ = -1;
+  unsigned ctx_rr_ = 0;        // round robin of the asynchronous device-resident launches
+  std::mutex occ_mu_;
   int kernel_pref_ = 0;        // env HNSW_B200_KERNEL=warp (A/B measurements): 1 = always the generic warp kernel
   bool zero_copy_ = true;      // env HNSW_B200_ZERO_COPY=0: explicit H2D / D2H copies instead of kernel access to pinned host memory
 
-  // small device scratch
+  // small device scratch (insert path; searches: SearchCtx)
   unsigned int* d_counter_ = nullptr;
   int* d_status_ = nullptr;
   unsigned long long* d_stats_ = nullptr;
   bool stats_on_ = false;
-  uint64_t stat_queries_ = 0;
+  std::atomic<uint64_t> stat_queries_{0};
 
-  // staging
+  // staging of the insert path
   void* h_pin_ = nullptr;
   size_t h_pin_bytes_ = 0;
-  void* h_res_ = nullptr;  // pinned result staging: NeighbourOut[nq*k], int32 counts[nq], int32 status
-  size_t h_res_bytes_ = 0;
   std::map<std::tuple<int, int, int, size_t>, int> occ_cache_;  // (filtered, queue kind, d4, smem) -> CTAs/SM
-  void* d_q_ = nullptr;
-  size_t d_q_bytes_ = 0;
-  void* d_out_ = nullptr;
-  size_t d_out_bytes_ = 0;
-  void* d_cnt_ = nullptr;
-  size_t d_cnt_bytes_ = 0;
-  void* d_fbits_ = nullptr;
-  size_t d_fbits_bytes_ = 0;
-  void* d_cbuf_ = nullptr;
-  size_t d_cbuf_bytes_ = 0;
   void* d_mask_ = nullptr;
   size_t d_mask_bytes_ = 0;
 };

@@ -13,11 +13,11 @@ inline int dtype_size(int dt) { return dt == DT_U8 ? 1 : dt == DT_U16 ? 2 : 4; }
 
 constexpr int SEARCH_THREADS = 256;  // 8 warps = 8 queries in flight per CTA
 constexpr int BUILD_THREADS = 128;   // 4 warps = 4 inserts in flight per CTA
-constexpr int LEAN_THREADS = 128;     // lean kernel (search_lean.cu): 4 warps = 4 queries in flight per CTA
+constexpr int LEAN_THREADS = 32;      // lean kernel (search_lean.cuh): one warp per CTA, so that a finished query frees its slot at once
 #ifndef HB_LEAN_BLOCKS
-#define HB_LEAN_BLOCKS 7
+#define HB_LEAN_BLOCKS 28
 #endif
-constexpr int LEAN_MIN_BLOCKS = HB_LEAN_BLOCKS;  // 7 CTAs x 4 warps = 28 warps per SM, <= 72 registers per thread (measured: 6, 7, 8 CTAs within 3 %)
+constexpr int LEAN_MIN_BLOCKS = HB_LEAN_BLOCKS;  // 28 one-warp CTAs per SM, <= 72 registers per thread (measured: 24, 28, 32 warps within 3 %)
 
 // One answer slot.  Same 16-byte layout as the reference's #[repr(C)] Neighbour_api {id: usize, d: f32}
 // (/root/reference/src/libext.rs:64-71); the internal id rides in what is tail padding there.

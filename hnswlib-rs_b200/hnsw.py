@@ -87,6 +87,8 @@ def load_library():
     L.hnsw_b200_search_device.argtypes = [vp, vp, u64, u64, u64, vp, vp, i32, vp]
     L.hnsw_b200_get_stats.argtypes = [vp, vp, i32]
     L.hnsw_b200_set_stream.argtypes = [vp, vp]
+    L.hnsw_b200_join.argtypes = [vp]
+    L.hnsw_b200_stream_wait_last.argtypes = [vp, vp]
     L.hnsw_b200_check_status.argtypes = [vp]
     L.hnsw_b200_export_points.argtypes = [vp, vp, vp, vp, vp]
     L.hnsw_b200_export_vectors.argtypes = [vp, vp]
@@ -367,6 +369,14 @@ class Hnsw:
 
     def set_stream(self, cuda_stream):
         self._chk(self._L.hnsw_b200_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def join(self):
+        """the handle's stream waits for every asynchronous search_device launch enqueued so far"""
+        self._chk(self._L.hnsw_b200_join(self._h))
+
+    def stream_wait_last(self, cuda_stream=None):
+        """`cuda_stream` (None = the handle's) waits for the most recent asynchronous search_device launch"""
+        self._chk(self._L.hnsw_b200_stream_wait_last(self._h, C.c_void_p(cuda_stream or 0)))
 
     def check_status(self):
         r = self._L.hnsw_b200_check_status(self._h)

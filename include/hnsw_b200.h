@@ -233,16 +233,22 @@ int hnsw_b200_search_flat(const void* h, const void* queries, uint64_t nq, uint6
                           hnsw_b200_filter_fn fn, void* ctx, uint64_t* out_ids, float* out_dist,
                           uint32_t* out_internal, int32_t* out_pid, int32_t* out_counts);
 
-/* Device-resident variant (kernel-only timing, multi-GPU sharding): d_queries [nq][dim] floats and
+/* Device-resident variant (kernel-only timing, multi-GPU sharding): d_queries [nq][dim] elements and
  * d_out (Neighbour_api[nq][knbn], internal id in the tail padding) / d_counts (int32[nq]) are
- * DEVICE pointers owned by the caller; the call enqueues on the index stream and returns without
- * synchronising unless sync != 0.  kernel_ms (may be NULL) receives the CUDA-event duration of the
- * search kernel when sync != 0. */
+ * DEVICE pointers owned by the caller.  sync != 0: returns when the answers are there; kernel_ms (may be
+ * NULL) receives the CUDA-event duration of the search kernel.  sync == 0: the launch is ordered AFTER
+ * everything enqueued so far on the handle's stream and runs on one of two alternating internal streams,
+ * so that consecutive launches overlap (the last, long searches of one launch leave most SMs idle); the
+ * handle's stream does not wait for it until hnsw_b200_join(h); hnsw_b200_stream_wait_last(h, s) makes
+ * stream s (NULL = the handle's) wait for the most recent launch only.  Use distinct output buffers for
+ * launches that may be in flight together. */
 int hnsw_b200_search_device(const void* h, const void* d_queries, uint64_t nq, uint64_t knbn,
                             uint64_t ef_search, void* d_out, int32_t* d_counts, int sync, float* kernel_ms);
 
 /* Run this handle's kernels and copies on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL
  * restores the handle's own stream), e.g. so that torch.cuda.Event on torch's current stream brackets them. */
+int hnsw_b200_join(void* h);
+int hnsw_b200_stream_wait_last(void* h, void* cuda_stream);
 int hnsw_b200_set_stream(void* h, void* cuda_stream);
 /* After asynchronous hnsw_b200_search_device calls: synchronise and report 1 if a per-warp visited table
  * overflowed (those answers are empty; re-run them with sync != 0, which grows the tables), 0 if not, <0 on error. */

@@ -15,9 +15,10 @@ metric is quoted on:
 
   value      queries/s, inputs resident in HBM, K launches timed with CUDA events on the launch stream
   e2e        the same metric through the C-ABI call a user makes with HOST buffers, H2D of the queries and D2H of the
-             answers inside the timed region: hnsw_b200_search_flat; at N > 1 ONE call on rank 0's handle after
-             hnsw_b200_replicate, the library sharding the batch over the N GPUs (e2e.per_rank: every rank calling
-             search_flat on its own shard).  e2e.row_pointers (N = 1): the reference's own entry point
+             answers inside the timed region: hnsw_b200_search_flat_submit / _wait with two batches in flight from one
+             host thread (e2e.sequential: one hnsw_b200_search_flat call at a time); at N > 1 ONE search_flat call on
+             rank 0's handle after hnsw_b200_replicate, the library sharding the batch over the N GPUs (e2e.per_rank:
+             every rank pipelining its own shard).  e2e.row_pointers (N = 1): the reference's own entry point
              parallel_search_neighbours_f32 with pageable row pointers and malloc'ed answers
   roofline   algorithmic bytes (E*d*4 + A*4 + d*4 + k*16 per query, E/A counted by the kernel itself and
              equal to the oracle's counters, tests/test_gpu_search.py) / kernel time vs measured HBM peak
@@ -449,26 +450,25 @@ def run_ours(a, rank, world, local_rank):
         bar()
         return time.perf_counter() - t0
 
-    def two_threads(call, steps):
-        """the steps issued by two host threads (even / odd): two batches in flight, the way a serving loop keeps the GPU
-        busy; the library runs concurrent searches of one index on separate contexts"""
-        def run(t):
-            for i in range(t, steps, 2):
-                call(i)
-        th = [threading.Thread(target=run, args=(t,)) for t in range(2)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-
-    # (1) every rank calls hnsw_b200_search_flat on its own shard (ids + distances + counts back in host memory)
+    # (1) every rank searches its own shard through the flat host call (ids + distances + counts back in host memory):
+    # sequentially (one hnsw_b200_search_flat call at a time), and pipelined (hnsw_b200_search_flat_submit / _wait, batch
+    # i+1 submitted before batch i's answers are collected: two batches in flight from ONE host thread)
     flat = lambda i: h.search_flat(qh_np[i % NB], a.k, a.ef, with_internal=False, with_pid=False)   # noqa: E731
     seq_s = timed(flat, a.steps, a.warmup)
-    for i in range(a.warmup):
-        flat(i)
+
+    def pipelined(steps):
+        prev = None
+        for i in range(steps):
+            t = h.submit_flat(qh_np[i % NB], a.k, a.ef, with_internal=False, with_pid=False)
+            if prev is not None:
+                h.wait_flat(prev)
+            prev = t
+        h.wait_flat(prev)
+
+    pipelined(a.warmup)
     barrier()
     t0 = time.perf_counter()
-    two_threads(flat, a.steps)
+    pipelined(a.steps)
     barrier()
     per_rank_s = time.perf_counter() - t0
     note('per-rank e2e done')
@@ -527,11 +527,11 @@ def run_ours(a, rank, world, local_rank):
            "d2h_bytes_per_step": total_per_step * a.k * 16 + total_per_step * 4,
            "call": ("one hnsw_b200_search_flat call on rank 0's handle after hnsw_b200_replicate: the library shards the "
                     f"batch of {total_per_step} queries over {world} GPUs" if multi else
-                    "hnsw_b200_search_flat, pinned host buffers (read and written by the kernel: zero-copy), two host "
-                    "threads issuing alternate steps = two batches in flight"),
-           "host_threads": 1 if multi else 2,
+                    "hnsw_b200_search_flat_submit / _wait, one host thread, batch i+1 submitted before batch i is collected "
+                    "(two batches in flight); pinned host buffers read and written by the kernel (zero-copy)"),
+           "host_threads": 1,
            "per_rank": {"value": e2e_per_rank, "unit": "queries/s",
-                        "call": "every rank: hnsw_b200_search_flat on its own shard, pinned host buffers, two host threads"},
+                        "call": "every rank: hnsw_b200_search_flat_submit / _wait on its own shard, two batches in flight"},
            "sequential": {"value": e2e_seq, "unit": "queries/s",
                           "call": "every rank: one hnsw_b200_search_flat call at a time (no batches in flight together)"}}
     if rowptr_s is not None:

@@ -42,7 +42,8 @@ static int pass(Index* ix, int r) {
 #define HB_H(h) \
   if (!(h)) return set_err("NULL handle"); \
   Index* ix = ((const AnyApi*)(h))->ix;    \
-  std::unique_lock<std::shared_mutex> g__(ix->mu)
+  std::unique_lock<std::shared_mutex> g__(ix->mu); \
+  ix->drain_pending()
 #define HB_HS(h) \
   if (!(h)) return set_err("NULL handle"); \
   Index* ix = ((const AnyApi*)(h))->ix;    \
@@ -98,6 +99,7 @@ static void insert_any(void* hv, size_t len, const void* data, size_t id) {
     return;
   }
   std::unique_lock<std::shared_mutex> g(h->ix->mu);
+  h->ix->drain_pending();
   if (pass(h->ix, h->ix->set_dim((int)len))) return;
   uint64_t id64 = id;
   pass(h->ix, h->ix->insert_batch(data, 1, len, nullptr, &id64, nullptr));
@@ -110,6 +112,7 @@ static void parallel_insert_any(void* hv, size_t nb_vec, size_t vec_len, const v
     return;
   }
   std::unique_lock<std::shared_mutex> g(h->ix->mu);
+  h->ix->drain_pending();
   if (pass(h->ix, h->ix->set_dim((int)vec_len))) return;
   std::vector<uint64_t> id64(ids, ids + nb_vec);
   pass(h->ix, h->ix->insert_batch(nullptr, nb_vec, vec_len, datas, id64.data(), nullptr));
@@ -519,6 +522,59 @@ int hnsw_b200_search_flat(const void* h, const void* queries, uint64_t nq, uint6
     return 0;
   };
   return pass(ix, use_shards(ix, nq) ? ix->for_each_shard(nq, run) : run(ix, 0, nq));
+}
+
+// Submit / wait: the same search with the call split in two, so that one host thread keeps several batches in flight
+// (batch i+1 is enqueued before batch i's answers are collected).  Unfiltered, one device.
+int64_t hnsw_b200_search_flat_submit(const void* h, const void* queries, uint64_t nq, uint64_t dim, uint64_t knbn,
+                                     uint64_t ef_search, uint64_t* out_ids, float* out_dist, uint32_t* out_internal,
+                                     int32_t* out_pid, int32_t* out_counts) {
+  HB_HS(h);
+  if (!queries || !out_ids || !out_dist || !out_counts || knbn == 0 || nq == 0) return set_err("bad argument");
+  const int ci = ix->acquire_ctx();
+  int r = ix->search_host_begin(ci, queries, nullptr, nq, (int)dim, knbn, ef_search, nullptr);
+  if (r) {
+    ix->release_ctx(ci);
+    return pass(ix, r);
+  }
+  Index::SearchCtx::Pending& p = ix->ctx(ci).pend;
+  p.u_ids = out_ids;
+  p.u_dist = out_dist;
+  p.u_internal = out_internal;
+  p.u_pid = out_pid;
+  p.u_counts = out_counts;
+  ix->pending_.fetch_add(1);
+  return ci;
+}
+
+int hnsw_b200_search_flat_wait(const void* h, int64_t ticket) {
+  if (!h) return set_err("NULL handle");
+  Index* ix = ((const AnyApi*)h)->ix;  // no lock: a writer holding the index exclusively is waiting for this very call
+  if (ticket < 0 || ticket >= Index::NCTX) return set_err("bad ticket");
+  const int ci = (int)ticket;
+  const NeighbourOut* tmp = nullptr;
+  const int32_t* cnts = nullptr;
+  int r = ix->search_host_finish(ci, &tmp, &cnts);
+  if (!r) {
+    const Index::SearchCtx::Pending& p = ix->ctx(ci).pend;
+    memcpy(p.u_counts, cnts, p.nq * sizeof(int32_t));
+    const uint64_t tot = p.nq * p.k;
+    for (uint64_t s = 0; s < tot; ++s) p.u_ids[s] = tmp[s].origin;
+    for (uint64_t s = 0; s < tot; ++s) p.u_dist[s] = tmp[s].dist;
+    if (p.u_internal)
+      for (uint64_t s = 0; s < tot; ++s) p.u_internal[s] = tmp[s].internal;
+    if (p.u_pid)
+      for (uint64_t s = 0; s < tot; ++s) {
+        const uint32_t it = tmp[s].internal;
+        p.u_pid[2 * s] = it != hb::INVALID_ID ? (int32_t)ix->h_level[it] : -1;
+        p.u_pid[2 * s + 1] = it != hb::INVALID_ID ? ix->h_rank[it] : -1;
+      }
+  } else {
+    g_err = ix->err();
+  }
+  ix->release_ctx(ci);
+  ix->pending_.fetch_sub(1);
+  return r;
 }
 
 int hnsw_b200_search_device(const void* h, const void* d_queries, uint64_t nq, uint64_t knbn,

@@ -756,12 +756,11 @@ static const void* device_view_of_host(const void* p) {
 // buffer: no cudaMemcpy before or after the launch, one synchronisation.  Pageable queries and row pointers are
 // gathered into the index's own pinned staging buffer first (the only host-side copy), which the kernel then reads
 // the same way.  zero_copy_ = false (env HNSW_B200_ZERO_COPY=0) restores explicit H2D / D2H copies.
-int Index::search_host_staged(int ci, const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
-                              const uint32_t* filter_bits_host, const NeighbourOut** out, const int32_t** counts) {
+int Index::search_host_begin(int ci, const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
+                             const uint32_t* filter_bits_host) {
   SearchCtx& c = ctx_[ci];
   cudaStream_t st = c.stream;
-  *out = nullptr;
-  *counts = nullptr;
+  c.pend = SearchCtx::Pending();
   if (nq == 0) return 0;
   HB_CUDA(cudaSetDevice(device));
   if (dim != 0 && d != dim) return fail("query length differs from the index dimension");
@@ -777,8 +776,14 @@ int Index::search_host_staged(int ci, const void* queries, const void* const* ro
   NeighbourOut* hout = (NeighbourOut*)c.h_res;
   int32_t* hcnt = (int32_t*)((char*)c.h_res + out_bytes);
   int32_t* hstatus = hcnt + nq;
-  *out = hout;
-  *counts = hcnt;
+  c.pend.hout = hout;
+  c.pend.hcnt = hcnt;
+  c.pend.hstatus = hstatus;
+  c.pend.nq = nq;
+  c.pend.k = k;
+  c.pend.ef = ef;
+  c.pend.out_bytes = out_bytes;
+  c.pend.cnt_bytes = cnt_bytes;
   if (dim == 0) {  // empty index: every answer is empty (hnsw.rs:1498-1500)
     for (size_t i = 0; i < nq; ++i) hcnt[i] = 0;
     for (size_t i = 0; i < nq * k; ++i) hout[i] = NeighbourOut{~0ull, __builtin_inff(), INVALID_ID};
@@ -830,21 +835,51 @@ int Index::search_host_staged(int ci, const void* queries, const void* const* ro
     HB_CUDA(cudaMemcpyAsync(c.d_fbits, filter_bits_host, fb, cudaMemcpyHostToDevice, st));
     dfb = (const uint32_t*)c.d_fbits;
   }
-  // one enqueue (copies if any, kernel, status), one synchronisation; the slow path (a visited table overflowed: grow
-  // and re-run) is taken only when the status says so
-  for (int pass = 0; pass < 2; ++pass) {
-    if ((r = search_on_ctx(c, d_queries, nq, k, ef, dfb, k_out, k_cnt, pass == 1, nullptr))) return r;
-    if (!dv) {
-      HB_CUDA(cudaMemcpyAsync(hout, c.d_out, out_bytes, cudaMemcpyDeviceToHost, st));
-      HB_CUDA(cudaMemcpyAsync(hcnt, c.d_cnt, cnt_bytes, cudaMemcpyDeviceToHost, st));
-    }
-    HB_CUDA(cudaMemcpyAsync(hstatus, c.d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  // one enqueue (copies if any, kernel, status); search_host_finish synchronises once and takes the slow path (a visited
+  // table overflowed: grow and re-run) only when the status says so
+  c.pend.d_queries = d_queries;
+  c.pend.dfb = dfb;
+  c.pend.k_out = k_out;
+  c.pend.k_cnt = k_cnt;
+  c.pend.direct = dv != nullptr;
+  c.pend.enqueued = true;
+  if ((r = search_on_ctx(c, d_queries, nq, k, ef, dfb, k_out, k_cnt, false, nullptr))) return r;
+  if (!c.pend.direct) {
+    HB_CUDA(cudaMemcpyAsync(hout, c.d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaMemcpyAsync(hcnt, c.d_cnt, cnt_bytes, cudaMemcpyDeviceToHost, st));
+  }
+  HB_CUDA(cudaMemcpyAsync(hstatus, c.d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+int Index::search_host_finish(int ci, const NeighbourOut** out, const int32_t** counts) {
+  SearchCtx& c = ctx_[ci];
+  cudaStream_t st = c.stream;
+  SearchCtx::Pending& p = c.pend;
+  *out = p.hout;
+  *counts = p.hcnt;
+  if (!p.enqueued) return 0;  // empty batch or empty index: the answers (if any) were filled by search_host_begin
+  HB_CUDA(cudaSetDevice(device));
+  HB_CUDA(cudaStreamSynchronize(st));
+  if (*p.hstatus == 0) return 0;
+  HB_CUDA(cudaMemsetAsync(c.d_status, 0, sizeof(int), st));
+  int r;
+  if ((r = search_on_ctx(c, p.d_queries, p.nq, p.k, p.ef, p.dfb, p.k_out, p.k_cnt, true, nullptr))) return r;  // grows the tables
+  if (!p.direct) {
+    HB_CUDA(cudaMemcpyAsync(p.hout, c.d_out, p.out_bytes, cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaMemcpyAsync(p.hcnt, c.d_cnt, p.cnt_bytes, cudaMemcpyDeviceToHost, st));
     HB_CUDA(cudaStreamSynchronize(st));
-    if (*hstatus == 0) break;
-    if (pass == 1) return fail("visited table overflow persists");
-    HB_CUDA(cudaMemsetAsync(c.d_status, 0, sizeof(int), st));
   }
   return 0;
+}
+
+int Index::search_host_staged(int ci, const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
+                              const uint32_t* filter_bits_host, const NeighbourOut** out, const int32_t** counts) {
+  *out = nullptr;
+  *counts = nullptr;
+  int r = search_host_begin(ci, queries, rows, nq, d, k, ef, filter_bits_host);
+  if (r) return r;
+  return search_host_finish(ci, out, counts);
 }
 
 int Index::search_host(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,

@@ -16,6 +16,7 @@
 #include <shared_mutex>
 #include <tuple>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
@@ -99,6 +100,14 @@ class Index {
   int search_host(const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
                   const uint32_t* filter_bits_host, NeighbourOut* out, int32_t* counts);
   // same on context c (a CtxLease), answers left in the context's pinned buffer (valid until the lease ends)
+  int search_host_begin(int c, const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
+                        const uint32_t* filter_bits_host);
+  int search_host_finish(int c, const NeighbourOut** out, const int32_t** counts);
+  // submitted-but-not-waited host searches: anything that changes the graph waits for them (drain_pending)
+  std::atomic<int> pending_{0};
+  void drain_pending() const {
+    while (pending_.load() != 0) std::this_thread::yield();
+  }
   int search_host_staged(int c, const void* queries, const void* const* rows, size_t nq, int d, size_t k, size_t ef,
                          const uint32_t* filter_bits_host, const NeighbourOut** out, const int32_t** counts);
   int search_device(const void* d_queries, size_t nq, size_t k, size_t ef, const uint32_t* d_filter_bits,
@@ -160,6 +169,19 @@ class Index {
     void *h_pin = nullptr, *h_res = nullptr;  // pinned, mapped: query staging / answers
     size_t h_pin_bytes = 0, h_res_bytes = 0;
     bool busy = false;
+    struct Pending {  // a host search enqueued by search_host_begin, completed by search_host_finish
+      const void* d_queries = nullptr;
+      const uint32_t* dfb = nullptr;
+      NeighbourOut *k_out = nullptr, *hout = nullptr;
+      int32_t *k_cnt = nullptr, *hcnt = nullptr, *hstatus = nullptr;
+      size_t nq = 0, k = 0, ef = 0, out_bytes = 0, cnt_bytes = 0;
+      bool direct = false, enqueued = false;
+      // where hnsw_b200_search_flat_wait unpacks to
+      uint64_t* u_ids = nullptr;
+      float* u_dist = nullptr;
+      uint32_t* u_internal = nullptr;
+      int32_t *u_pid = nullptr, *u_counts = nullptr;
+    } pend;
   };
   static constexpr int NCTX = 4;    // leased by synchronous calls (host threads)
   static constexpr int NASYNC = 2;  // alternated by asynchronous device-resident launches (never leased)

@@ -85,6 +85,9 @@ def load_library():
     L.hnsw_b200_insert_flat.argtypes = [vp, vp, u64, u64, vp, vp]
     L.hnsw_b200_search_flat.argtypes = [vp, vp, u64, u64, u64, u64, i32, vp, u64, FILTER_FN, vp, vp, vp, vp, vp, vp]
     L.hnsw_b200_search_device.argtypes = [vp, vp, u64, u64, u64, vp, vp, i32, vp]
+    L.hnsw_b200_search_flat_submit.restype = i64
+    L.hnsw_b200_search_flat_submit.argtypes = [vp, vp, u64, u64, u64, u64, vp, vp, vp, vp, vp]
+    L.hnsw_b200_search_flat_wait.argtypes = [vp, i64]
     L.hnsw_b200_get_stats.argtypes = [vp, vp, i32]
     L.hnsw_b200_set_stream.argtypes = [vp, vp]
     L.hnsw_b200_join.argtypes = [vp]
@@ -325,6 +328,25 @@ class Hnsw:
                 nf = len(fids)
         self._chk(self._L.hnsw_b200_search_flat(self._h, _p(q), nq, d, int(knbn), int(ef), mode, _p(fids), nf, cb, None,
                                                 _p(o), _p(ds), _p(it), _p(pid), _p(cnt)))
+        return o, ds, it, pid, cnt
+
+    def submit_flat(self, queries, knbn, ef, with_internal=True, with_pid=True):
+        """hnsw_b200_search_flat_submit: enqueue a batch, return a ticket for wait_flat (up to 4 outstanding)"""
+        q = np.ascontiguousarray(queries, self.dtype)
+        nq, d = q.shape
+        o = np.empty((nq, knbn), np.uint64)
+        ds = np.empty((nq, knbn), np.float32)
+        it = np.empty((nq, knbn), np.uint32) if with_internal else None
+        pid = np.empty((nq, knbn, 2), np.int32) if with_pid else None
+        cnt = np.empty(nq, np.int32)
+        t = self._L.hnsw_b200_search_flat_submit(self._h, _p(q), nq, d, int(knbn), int(ef), _p(o), _p(ds), _p(it), _p(pid), _p(cnt))
+        if t < 0:
+            raise HnswError(last_error())
+        return (int(t), q, o, ds, it, pid, cnt)
+
+    def wait_flat(self, ticket):
+        t, _q, o, ds, it, pid, cnt = ticket
+        self._chk(self._L.hnsw_b200_search_flat_wait(self._h, t))
         return o, ds, it, pid, cnt
 
     def file_dump(self, path, basename, overwrite=True):

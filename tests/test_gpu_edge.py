@@ -193,3 +193,30 @@ def test_corrupt_dump_header_returns_null(pkg, tmp_path):
     g.write_bytes(bytes(raw))
     with pytest.raises(pkg.HnswError):
         pkg.Hnsw.load(tmp_path, base, "DistL2")
+
+
+def test_submit_wait_pipelines_batches(pkg, po):
+    """hnsw_b200_search_flat_submit / _wait: same answers as the one-call form, several tickets outstanding, and a call
+    that changes the index waits for the outstanding tickets instead of racing them"""
+    X = pkg.datagen.clustered(5000, 32, 1)
+    h = pkg.Hnsw(12, 6000, 16, 80, "DistL2")
+    h.insert_flat(X)
+    Qs = [pkg.datagen.clustered(700 + 13 * i, 32, 10 + i) for i in range(6)]
+    want = [h.search_flat(q, 7, 40) for q in Qs]
+    tickets = [h.submit_flat(q, 7, 40) for q in Qs[:4]]            # four in flight (the per-handle maximum)
+    got = [h.wait_flat(t) for t in tickets]
+    got += [h.wait_flat(h.submit_flat(q, 7, 40)) for q in Qs[4:]]
+    for w, g in zip(want, got):
+        for a, b in zip(w, g):
+            assert np.array_equal(a, b)
+    # a writer waits for outstanding tickets: insert from another thread while a ticket is open
+    t = h.submit_flat(Qs[0], 7, 40)
+    done = []
+    th = threading.Thread(target=lambda: (h.insert_flat(pkg.datagen.clustered(200, 32, 99), ids=np.arange(5000, 5200, dtype=np.uint64)),
+                                          done.append(1)))
+    th.start()
+    res = h.wait_flat(t)
+    th.join(timeout=60)
+    assert done == [1] and h.get_nb_point() == 5200
+    for a, b in zip(want[0], res):
+        assert np.array_equal(a, b)                               # the ticket saw the index as it was at submit time

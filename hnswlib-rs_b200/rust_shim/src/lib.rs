@@ -48,6 +48,9 @@ extern "C" {
     fn hnsw_b200_modify_level_scale(h: *mut HnswApif32, scale: f64) -> c_int;
     fn hnsw_b200_set_searching_mode(h: *mut HnswApif32, flag: c_int) -> c_int;
     fn hnsw_b200_get_nb_point(h: *const HnswApif32) -> u64;
+    // multi-GPU (include/hnsw_b200.h "Multi-GPU search"): one process drives several devices
+    fn hnsw_b200_replicate(h: *mut HnswApif32, ndev: c_int, devices: *const c_int) -> c_int;
+    fn hnsw_b200_replica_count(h: *const HnswApif32) -> c_int;
 }
 
 /// hnsw.rs:46
@@ -109,6 +112,13 @@ impl<D: DistName> Hnsw<D> {
     pub fn set_keeping_pruned(&mut self, flag: bool) { unsafe { hnsw_b200_set_keeping_pruned(self.h, flag as c_int); } }
     pub fn modify_level_scale(&mut self, s: f64) { unsafe { hnsw_b200_modify_level_scale(self.h, s); } }
     pub fn set_searching_mode(&mut self, flag: bool) { unsafe { hnsw_b200_set_searching_mode(self.h, flag as c_int); } }
+    /// Extension: copy the index to `devices[1..]` (devices[0] = the device it lives on); `parallel_search` then shards its
+    /// batch over all of them, one call as on the CPU (hnsw.rs:1612-1635).
+    pub fn replicate(&mut self, devices: &[i32]) -> Result<(), i32> {
+        let r = unsafe { hnsw_b200_replicate(self.h, devices.len() as c_int, devices.as_ptr()) };
+        if r == 0 { Ok(()) } else { Err(r) }
+    }
+    pub fn replica_count(&self) -> usize { unsafe { hnsw_b200_replica_count(self.h) as usize } }
 
     /// hnsw.rs:1069-1071
     pub fn insert(&self, datav_with_id: (&[f32], usize)) {

@@ -453,6 +453,12 @@ int hnsw_b200_modify_level_scale(void* h, double scale) {
   ix->level_scale = scale / std::log((double)ix->M);
   return 0;
 }
+int hnsw_b200_set_tie_mode(void* h, int mode) {
+  HB_H(h);
+  if (mode != 0 && mode != 1) return set_err("tie mode must be 0 (distance, id) or 1 (reference std heaps)");
+  ix->tie_std_ = mode == 1;
+  return 0;
+}
 int hnsw_b200_set_searching_mode(void* h, int flag) {
   HB_H(h);
   ix->searching = flag != 0;

@@ -667,10 +667,13 @@ int Index::search_on_ctx(SearchCtx& c, const void* d_queries, size_t nq, size_t 
   p.status = c.d_status;
   const bool filtered = d_filter_bits != nullptr;
   // kernel choice: lean (search_lean.cuh) whenever it applies, else the generic warp kernel (search.cu / filter.cu)
-  const bool lean = !filtered && kernel_pref_ == 0 && entry != INVALID_ID && lean_eligible(p.g.d4, p.ef) && lean_op_supported(metric, dtype);
-  p.q_kind = (filtered || lean) ? 0 : queue_kind(p.ef, metric, dtype);
-  p.q_smem = lean ? lean_queue_slots(p.ef) : queue_slots(p.q_kind, p.ef);
-  size_t spw = lean ? lean_smem_per_warp(p.q_smem) : search_smem_per_warp(p.g.d4, p.q_smem);
+  // tie mode "std" (search_std.cu): the reference's heaps replayed literally, unfiltered searches only
+  const bool stdtie = tie_std_ && !filtered;
+  const bool lean = !stdtie && !filtered && kernel_pref_ == 0 && entry != INVALID_ID && lean_eligible(p.g.d4, p.ef) && lean_op_supported(metric, dtype);
+  p.q_kind = (filtered || lean || stdtie) ? 0 : queue_kind(p.ef, metric, dtype);
+  p.q_smem = stdtie ? p.ef + 2 : (lean ? lean_queue_slots(p.ef) : queue_slots(p.q_kind, p.ef));
+  size_t spw = stdtie ? (((size_t)p.g.d4 * 16 + (size_t)p.q_smem * 8 + 256 + 127) & ~(size_t)127)
+                      : (lean ? lean_smem_per_warp(p.q_smem) : search_smem_per_warp(p.g.d4, p.q_smem));
   p.smem_per_warp = (int)spw;
   const int wpb = (lean ? LEAN_THREADS : SEARCH_THREADS) / 32;
   const size_t smem = spw * wpb;
@@ -680,12 +683,13 @@ int Index::search_on_ctx(SearchCtx& c, const void* d_queries, size_t nq, size_t 
   int bps = 0;
   {
     std::lock_guard<std::mutex> lk(occ_mu_);
-    const auto key = std::make_tuple(lean ? 3 : (int)filtered, lean ? p.q_smem : p.q_kind, p.g.d4, smem);
+    const auto key = std::make_tuple(stdtie ? 4 : (lean ? 3 : (int)filtered), lean ? p.q_smem : p.q_kind, p.g.d4, smem);
     auto it = occ_cache_.find(key);
     if (it != occ_cache_.end()) {
       bps = it->second;
     } else {
-      if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, 0, smem, st, true, &bps));
+      if (stdtie) HB_CUDA(launch_search_std(p, metric, dtype, 0, smem, st, true, &bps));
+      else if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, 0, smem, st, true, &bps));
       else if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, 0, smem, st, true, &bps));
       else HB_CUDA(launch_search(p, metric, dtype, 0, smem, st, true, &bps));
       occ_cache_[key] = bps;
@@ -711,14 +715,15 @@ int Index::search_on_ctx(SearchCtx& c, const void* d_queries, size_t nq, size_t 
     }
     if ((r = ensure_visited(pool, (size_t)grid * per_cta, vcap, st))) return r;
     if ((r = fill_visited_cfg(pool, p.vis, st))) return r;
-    if (filtered) {
+    if (filtered || stdtie) {  // candidate queue C: one region per warp slot
       if ((r = ensure_scratch(&c.d_cbuf, &c.d_cbuf_bytes, (size_t)grid * wpb * pool.cap * 8, st))) return r;
       p.cbuf = (uint64_t*)c.d_cbuf;
       p.ccap = (uint32_t)pool.cap;
     }
     HB_CUDA(cudaMemsetAsync(c.d_counter, 0, sizeof(unsigned int), st));
     HB_CUDA(cudaEventRecord(c.ev0, st));
-    if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, grid, smem, st, false, nullptr));
+    if (stdtie) HB_CUDA(launch_search_std(p, metric, dtype, grid, smem, st, false, nullptr));
+    else if (lean) HB_CUDA(launch_search_lean(p, metric, dtype, grid, smem, st, false, nullptr));
     else if (filtered) HB_CUDA(launch_search_filtered(p, metric, dtype, grid, smem, st, false, nullptr));
     else HB_CUDA(launch_search(p, metric, dtype, grid, smem, st, false, nullptr));
     HB_CUDA(cudaEventRecord(c.ev1, st));

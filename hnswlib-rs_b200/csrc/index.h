@@ -72,6 +72,7 @@ class Index {
   int M, max_layer, ef_c, metric, dtype, es, device;  // es = bytes per element
   size_t max_elements;
   bool extend_candidates = false, keep_pruned = false, searching = false;
+  bool tie_std_ = false;  // hnsw_b200_set_tie_mode: equal-distance ties resolved like the reference's std BinaryHeaps (search_std.cu)
   double level_scale;  // 1/ln(M) * factor
   SplitMix64 rng{397};
   uint32_t batch_ratio = 16, batch_max = 16384;

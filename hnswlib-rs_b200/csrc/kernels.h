@@ -107,6 +107,8 @@ cudaError_t launch_search_filtered(const SearchParams& p, int metric, int dtype,
                                    bool query_only, int* blocks_per_sm);
 cudaError_t launch_search(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st, bool query_only,
                           int* blocks_per_sm);
+cudaError_t launch_search_std(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st, bool query_only,
+                              int* blocks_per_sm);
 cudaError_t launch_search_lean(const SearchParams& p, int metric, int dtype, int grid, size_t smem, cudaStream_t st,
                                bool query_only, int* blocks_per_sm);
 cudaError_t launch_search_lean_u8(const SearchParams& p, int metric, int grid, size_t smem, cudaStream_t st, bool query_only,

@@ -73,7 +73,7 @@ def load_library():
     L.hnsw_b200_set_device.argtypes = [i32]
     L.hnsw_b200_free_neighbourhood.argtypes = [vp]
     L.hnsw_b200_free_vec_api.argtypes = [vp]
-    for name in ("set_extend_candidates", "set_keeping_pruned", "set_searching_mode", "enable_stats"):
+    for name in ("set_extend_candidates", "set_keeping_pruned", "set_searching_mode", "enable_stats", "set_tie_mode"):
         getattr(L, "hnsw_b200_" + name).argtypes = [vp, i32]
     L.hnsw_b200_modify_level_scale.argtypes = [vp, C.c_double]
     L.hnsw_b200_set_level_seed.argtypes = [vp, u64]
@@ -383,6 +383,10 @@ class Hnsw:
     # ---- statistics / graph transfer (extensions)
     def enable_stats(self, on=True):
         self._chk(self._L.hnsw_b200_enable_stats(self._h, int(on)))
+
+    def set_tie_mode(self, mode):
+        """0: ties by (distance, id); 1: the reference's std-BinaryHeap tie behaviour (hnsw_b200_set_tie_mode)"""
+        self._chk(self._L.hnsw_b200_set_tie_mode(self._h, int(mode)))
 
     def get_stats(self, reset=True):
         out = np.zeros(4, np.uint64)

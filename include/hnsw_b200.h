@@ -208,6 +208,11 @@ int hnsw_b200_set_extend_candidates(void* h, int flag);  /* hnsw.rs:858 */
 int hnsw_b200_set_keeping_pruned(void* h, int flag);     /* hnsw.rs:845 */
 int hnsw_b200_modify_level_scale(void* h, double scale); /* hnsw.rs:876-905, scale in [0.2,1] */
 int hnsw_b200_set_searching_mode(void* h, int flag);     /* hnsw.rs:834 */
+/* How unfiltered searches order EQUAL distances.  0 (default): by (distance, internal id), a total order; identical to the
+ * reference whenever no two compared distances are equal.  1: the reference's own behaviour, its two std BinaryHeaps
+ * (Ord = distance only, /root/reference/src/hnsw.rs:273-297, 940-1053, 1544) replayed literally: same neighbour ids as the
+ * reference on tie-heavy metrics (Hamming, Jaccard, integer L1), several times slower (one lane drives the heaps). */
+int hnsw_b200_set_tie_mode(void* h, int mode);
 int hnsw_b200_set_level_seed(void* h, uint64_t seed);
 uint64_t hnsw_b200_get_nb_point(const void* h);          /* hnsw.rs:810 */
 int hnsw_b200_get_max_level_observed(const void* h);     /* hnsw.rs:474 */

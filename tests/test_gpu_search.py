@@ -258,3 +258,60 @@ def test_probability_metrics_match_reference_order_oracle(pkg, po, metric):
     same = oi == gi
     assert same.mean() > 0.99
     assert np.allclose(gd[same], od[same], rtol=1e-5, atol=1e-7)
+
+
+STD_TIE_CASES = [c for c in INT_CASES if c[1] in ("DistHamming", "DistJaccard")] + [(np.uint16, "DistL1", 30, 6)]
+
+
+@pytest.mark.parametrize("dtype,metric,d,vrange", STD_TIE_CASES)
+def test_integer_types_match_std_oracle_in_tie_mode(pkg, po, dtype, metric, d, vrange):
+    """BASELINE.json: "identical neighbour-id sets for integer Hamming/Jaccard".  With hnsw_b200_set_tie_mode(h, 1) the GPU
+    replays the reference's std BinaryHeaps (search_std.cu), so on the SAME graph its answers must equal the literal-reference
+    oracle (MODE_STD: distance-only Ord, std sift rules): ids, distances, counts and the traversal counters."""
+    n, M, efc, k, ef = 1500, 8, 48, 10, 32
+    rng = np.random.default_rng(5)
+    X = rng.integers(0, vrange, (n, d)).astype(dtype)
+    Q = rng.integers(0, vrange, (300, d)).astype(dtype)
+    o = po.Oracle(M, n, 16, efc, metric, d, dtype=dtype, mode=po.MODE_STD, order=po.ORDER_GPU)
+    o.insert_batch(X)                                   # the literal reference build (serial)
+    lv, rk, og = o.export_points()
+    h = pkg.Hnsw(M, n, 16, efc, metric, dtype=dtype)
+    h.import_graph(X, og, lv, o.entry, oracle_layers(o))
+    o.counters()
+    oo, od, oi, opid, oc = o.search_batch(Q, k, ef)
+    co = o.counters()
+    det = h.search_flat(Q, k, ef)                       # default tie mode, for the report below
+    h.set_tie_mode(1)
+    h.enable_stats(True)
+    h.get_stats()
+    go, gd, gi, gpid, gc = h.search_flat(Q, k, ef)
+    cg = h.get_stats()
+    assert np.array_equal(gc, oc)
+    assert np.array_equal(gi, oi), "ids differ from the literal-reference oracle"
+    assert np.array_equal(go, oo) and np.array_equal(gpid, opid)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    for key in ("evals", "expansions", "adj_read"):
+        assert cg[key] == co[key], (key, cg, co)
+    # the reference's typed entry point takes the same path
+    par = h.parallel_search([q for q in Q[:5]], k, ef)
+    for i in range(5):
+        assert [x.d_id for x in par[i]] == oo[i, :oc[i]].tolist()
+    # and the default mode differs only by tie resolution: same distance at every rank for nearly every query
+    same_d = np.mean(np.all(det[1] == gd, axis=1))
+    same_ids = np.mean(np.all(det[2] == gi, axis=1))
+    print(f"{metric} {np.dtype(dtype).name}: default tie mode returns the same distance list for {same_d:.2%} of the queries, "
+          f"the same id list for {same_ids:.2%}")
+    h.set_tie_mode(0)
+    back = h.search_flat(Q, k, ef)
+    assert np.array_equal(back[2], det[2])
+
+
+def test_tie_mode_std_equals_default_without_ties(pkg, po):
+    """on data without equal distances both tie modes are the reference: identical answers"""
+    X, o, h = build_pair(pkg, po, 4000, 24, 12, 64, "DistL2", "clustered")
+    Q = pkg.datagen.clustered(300, 24, 3)
+    a = h.search_flat(Q, 10, 48)
+    h.set_tie_mode(1)
+    b = h.search_flat(Q, 10, 48)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)

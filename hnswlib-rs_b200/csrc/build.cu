@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) insert_search_kernel(InsertPara
   off += (size_t)nbmax * 4;
   uint16_t* disc = reinterpret_cast<uint16_t*>(base + off);
 
-  const uint32_t slot = blockIdx.x * (BUILD_THREADS / 32) + warp;
+  const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + warp;
   Visited vis;
   vis.init(p.vis, slot);
   Queue Q;
@@ -342,10 +342,10 @@ static cudaError_t launch_insert_for_op(const InsertParams& p, int grid, size_t 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                     \
     if (blocks_per_sm) {                                                                                \
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, BUILD_THREADS, smem);      \
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, p.threads, smem);      \
       if (e != cudaSuccess) return e;                                                                   \
     }                                                                                                   \
-    if (!query_only) kern<<<grid, BUILD_THREADS, smem, st>>>(p);                                        \
+    if (!query_only) kern<<<grid, p.threads, smem, st>>>(p);                                        \
     return cudaGetLastError();                                                                          \
   } while (0)
   if constexpr (Specialise<Op>::value) {

@@ -441,6 +441,10 @@ int hnsw_b200_set_extend_candidates(void* h, int flag) {
   ix->extend_candidates = flag != 0;
   return 0;
 }
+int hnsw_b200_get_extend_candidates(const void* h) {
+  if (!h) return set_err("NULL handle");
+  return ((const AnyApi*)h)->ix->extend_candidates ? 1 : 0;
+}
 int hnsw_b200_set_keeping_pruned(void* h, int flag) {
   HB_H(h);
   ix->keep_pruned = flag != 0;

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_filter_kernel(SearchPar
   s.wbuf = reinterpret_cast<uint64_t*>(base + stb + (size_t)g.d4 * 16);
   s.cand_id = reinterpret_cast<uint32_t*>(base + stb + (size_t)g.d4 * 16 + (size_t)p.q_smem * 8);
   s.cand_d = reinterpret_cast<float*>(s.cand_id + 32);
-  const uint32_t slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
+  const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + warp;  // the host launches fewer warps per CTA when shared memory is short
   Visited vis;
   vis.init(p.vis, slot);
   uint64_t* cbuf = p.cbuf + (size_t)slot * p.ccap;
@@ -265,10 +265,10 @@ static cudaError_t launch_filter_for_op(const SearchParams& p, int grid, size_t 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                     \
     if (blocks_per_sm) {                                                                                \
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, SEARCH_THREADS, smem);     \
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, p.threads, smem);     \
       if (e != cudaSuccess) return e;                                                                   \
     }                                                                                                   \
-    if (!query_only) kern<<<grid, SEARCH_THREADS, smem, st>>>(p);                                       \
+    if (!query_only) kern<<<grid, p.threads, smem, st>>>(p);                                       \
     return cudaGetLastError();                                                                          \
   } while (0)
   if constexpr (Specialise<Op>::value) {

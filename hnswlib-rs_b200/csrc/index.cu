@@ -280,8 +280,9 @@ int Index::grow_plevel(uint32_t id, int new_pl) {
 int Index::check_insert_fit() {
   int qk = queue_kind(ef_c, metric, dtype);
   if (qk != 0 && qk < 104) qk = 104;
-  const size_t smem = insert_smem_per_warp(row_bytes / 16, ef_c, 2 * M, queue_slots(qk, ef_c)) * (BUILD_THREADS / 32);
-  if (smem > 220 * 1024) return fail("ef_construction / dimension too large for the insert kernel's shared memory");
+  const size_t spw = insert_smem_per_warp(row_bytes / 16, ef_c, 2 * M, queue_slots(qk, ef_c));
+  if (spw > 220 * 1024)
+    return fail("ef_construction / dimension too large: one insert needs " + std::to_string(spw) + " bytes of shared memory (limit 220 KB)");
   return 0;
 }
 
@@ -320,12 +321,14 @@ int Index::run_insert_range(size_t first, size_t count, const std::vector<uint16
   p.q_smem = queue_slots(p.q_kind, ef_c);
   const size_t spw = insert_smem_per_warp(p.g.d4, ef_c, p.g.deg0, p.q_smem);
   p.smem_per_warp = (int)spw;
-  const size_t smem = spw * (BUILD_THREADS / 32);
+  int wpb = BUILD_THREADS / 32;
+  while (wpb > 1 && spw * wpb > 220 * 1024) wpb >>= 1;  // fewer inserts per CTA when one warp's share is large
+  const size_t smem = spw * wpb;
   if (smem > 220 * 1024) return fail("ef_construction / dimension too large for the insert kernel's shared memory");
+  p.threads = wpb * 32;
   int bps = 0;
   HB_CUDA(launch_insert_search(p, metric, dtype, 0, smem, stream_, true, &bps));
   if (bps < 1) return fail("insert kernel does not fit on an SM");
-  const int wpb = BUILD_THREADS / 32;
   int grid = (int)std::min<size_t>((size_t)sm_count_ * bps, (count + wpb - 1) / wpb);
   size_t vcap = next_pow2(std::max<size_t>(1024, (size_t)2 * (ef_c + 16) * p.g.deg0));
   for (int attempt = 0;; ++attempt) {
@@ -675,15 +678,20 @@ int Index::search_on_ctx(SearchCtx& c, const void* d_queries, size_t nq, size_t 
   size_t spw = stdtie ? (((size_t)p.g.d4 * 16 + (size_t)p.q_smem * 8 + 256 + 127) & ~(size_t)127)
                       : (lean ? lean_smem_per_warp(p.q_smem) : search_smem_per_warp(p.g.d4, p.q_smem));
   p.smem_per_warp = (int)spw;
-  const int wpb = (lean ? LEAN_THREADS : SEARCH_THREADS) / 32;
+  // warps per CTA: as many as the kernel is built for, fewer when one warp's share of shared memory is large (wide rows,
+  // big ef); a single warp must fit
+  int wpb = (lean ? LEAN_THREADS : SEARCH_THREADS) / 32;
+  while (wpb > 1 && spw * wpb > 220 * 1024) wpb >>= 1;
   const size_t smem = spw * wpb;
-  if (smem > 220 * 1024) return fail("ef / dimension too large for the search kernel's shared memory");
+  if (smem > 220 * 1024)
+    return fail("ef / dimension too large: one query needs " + std::to_string(spw) + " bytes of shared memory (limit 220 KB)");
+  p.threads = wpb * 32;
   p.cbuf = nullptr;
   p.ccap = 0;
   int bps = 0;
   {
     std::lock_guard<std::mutex> lk(occ_mu_);
-    const auto key = std::make_tuple(stdtie ? 4 : (lean ? 3 : (int)filtered), lean ? p.q_smem : p.q_kind, p.g.d4, smem);
+    const auto key = std::make_tuple(stdtie ? 4 : (lean ? 3 : (int)filtered), (lean ? p.q_smem : p.q_kind) * 64 + wpb, p.g.d4, smem);
     auto it = occ_cache_.find(key);
     if (it != occ_cache_.end()) {
       bps = it->second;

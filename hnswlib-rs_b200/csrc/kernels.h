@@ -44,6 +44,7 @@ struct SearchParams {
   unsigned long long* stats;    // nullptr or [3]: evals, expansions, adjacency ids read
   int* status;                  // set to 1 on visited-table overflow
   int smem_per_warp;
+  int threads;  // threads per CTA of this launch (a multiple of 32)
   int q_smem;  // queue slots in shared memory
   int q_kind;  // QueueSel kind
   uint64_t* cbuf;  // filtered search only: candidate queue C, [slots][ccap] keys
@@ -90,6 +91,7 @@ struct InsertParams {
   unsigned long long* stats;
   int* status;
   int smem_per_warp;
+  int threads;  // threads per CTA of the search phase (a multiple of 32)
   int q_smem;
   int q_kind;
 };

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 4) search_kernel(SearchParams 
   if (lane == 0) mbar_init(stg.bar, 1);
   __syncwarp();
 
-  const uint32_t slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
+  const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + warp;  // the host launches fewer warps per CTA when shared memory is short
   Visited vis;
   vis.init(p.vis, slot);
   Queue Q;
@@ -130,10 +130,10 @@ static cudaError_t launch_for_op(const SearchParams& p, int grid, size_t smem, c
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
     if (e != cudaSuccess) return e;                                                                             \
     if (blocks_per_sm) {                                                                                        \
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, SEARCH_THREADS, smem);             \
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, p.threads, smem);             \
       if (e != cudaSuccess) return e;                                                                           \
     }                                                                                                           \
-    if (!query_only) kern<<<grid, SEARCH_THREADS, smem, st>>>(p);                                               \
+    if (!query_only) kern<<<grid, p.threads, smem, st>>>(p);                                               \
     return cudaGetLastError();                                                                                  \
   } while (0)
   if constexpr (Specialise<Op>::value) {

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_std_kernel(SearchParams
   SItem* wv = reinterpret_cast<SItem*>(base + (size_t)g.d4 * 16);
   uint32_t* cand_id = reinterpret_cast<uint32_t*>(base + (size_t)g.d4 * 16 + (size_t)p.q_smem * 8);
   float* cand_d = reinterpret_cast<float*>(cand_id + 32);
-  const uint32_t slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
+  const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + warp;  // the host launches fewer warps per CTA when shared memory is short
   Visited vis;
   vis.init(p.vis, slot);
   SItem* cv = reinterpret_cast<SItem*>(p.cbuf + (size_t)slot * p.ccap);
@@ -279,10 +279,10 @@ cudaError_t launch_search_std(const SearchParams& p, int metric, int dtype, int 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (blocks_per_sm) {
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, SEARCH_THREADS, smem);
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, p.threads, smem);
       if (e != cudaSuccess) return e;
     }
-    if (!query_only) kern<<<grid, SEARCH_THREADS, smem, st>>>(p);
+    if (!query_only) kern<<<grid, p.threads, smem, st>>>(p);
     return cudaGetLastError();
   });
 }

@@ -75,6 +75,7 @@ def load_library():
     L.hnsw_b200_free_vec_api.argtypes = [vp]
     for name in ("set_extend_candidates", "set_keeping_pruned", "set_searching_mode", "enable_stats", "set_tie_mode"):
         getattr(L, "hnsw_b200_" + name).argtypes = [vp, i32]
+    L.hnsw_b200_get_extend_candidates.argtypes = [vp]
     L.hnsw_b200_modify_level_scale.argtypes = [vp, C.c_double]
     L.hnsw_b200_set_level_seed.argtypes = [vp, u64]
     L.hnsw_b200_get_nb_point.restype = u64

@@ -197,6 +197,9 @@ void hnsw_b200_drop(const void* h);
 
 const char* hnsw_b200_last_error(void);
 int hnsw_b200_device_count(void);
+/* Limits: max_nb_connection <= 256; fewer than 2^31 points; one query (or insert) must fit 220 KB of shared memory:
+ * 16 * ceil(dim * sizeof(T) / 128) * 8 bytes for the query (twice that for an insert) plus 8 bytes per ef (ef_construction)
+ * slot, i.e. dimensions up to ~13 000 f32 at ef = 64.  Wide rows or big ef make the kernels run fewer warps per block, not fail. */
 /* select the CUDA device used by handles created afterwards on this thread's process (default 0) */
 int hnsw_b200_set_device(int device);
 
@@ -205,6 +208,12 @@ void hnsw_b200_free_vec_api(const Vec_api_Neighbourhood_api* p);
 
 /* Hnsw setters/getters, /root/reference/src/hnsw.rs:810-905 */
 int hnsw_b200_set_extend_candidates(void* h, int flag);  /* hnsw.rs:858 */
+/* The flag as the engine applies it.  The reference turns it on at every reload (hnswio.rs:510, 599); the engine can honour
+ * it only when ef_construction > 2 * max_nb_connection (select_neighbours extends only when it holds <= max neighbours
+ * candidates, hnsw.rs:1318-1362, which with such an ef means the search ran out of reachable points and the extension set is
+ * empty): after reloading an index built with a smaller ef_construction this returns 0, and inserts into it keep every
+ * candidate where the reference would run the extension + heuristic. */
+int hnsw_b200_get_extend_candidates(const void* h);
 int hnsw_b200_set_keeping_pruned(void* h, int flag);     /* hnsw.rs:845 */
 int hnsw_b200_modify_level_scale(void* h, double scale); /* hnsw.rs:876-905, scale in [0.2,1] */
 int hnsw_b200_set_searching_mode(void* h, int flag);     /* hnsw.rs:834 */

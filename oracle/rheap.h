@@ -11,7 +11,7 @@
 // when `left <= right`, then sift_up; into_sorted_vec -> swap(0,end) + sift_down_range;
 // retain -> Vec::retain + rebuild_tail).  Restated from the published algorithm; the Rust
 // toolchain is absent here so this restatement is pinned only by the unit checks in
-// tests/test_oracle_rheap.py ("parity unpinned" w.r.t. the real std).
+// tests/test_oracle.py (test_rheap_*) ("parity unpinned" w.r.t. the real std).
 #pragma once
 #include <cstddef>
 #include <cstdint>

@@ -220,3 +220,24 @@ def test_submit_wait_pipelines_batches(pkg, po):
     assert done == [1] and h.get_nb_point() == 5200
     for a, b in zip(want[0], res):
         assert np.array_equal(a, b)                               # the ticket saw the index as it was at submit time
+
+
+def test_very_wide_rows_run_with_fewer_warps_per_block(pkg, po):
+    """d = 7000 f32 (28 KB per row): 8 warps' worth of query rows no longer fit one block's shared memory; the kernels run
+    fewer warps per block instead of failing, and the answers still equal the oracle's"""
+    n, d = 400, 7000
+    X = pkg.datagen.uniform(n, d, 1)
+    o = po.Oracle(8, n, 16, 40, "DistL2", d, mode=po.MODE_DET, order=po.ORDER_GPU)
+    lv = o.draw_levels(n)
+    o.insert_batch(X, levels=lv)
+    h = pkg.Hnsw(8, n, 16, 40, "DistL2")
+    h.set_insert_batching(1 << 30, 1)
+    h.insert_flat(X, levels=lv)
+    for l in range(2):
+        for a, b in zip(h.export_layer(l)[:2], o.export_layer(l)[:2]):
+            assert np.array_equal(a, b)
+    Q = pkg.datagen.uniform(40, d, 2)
+    go, gd, gi, _, gc = h.search_flat(Q, 5, 32)
+    oo, od, oi, _, oc = o.search_batch(Q, 5, 32)
+    assert np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    assert pkg.load_library().hnsw_b200_get_extend_candidates(h._h) == 0

@@ -338,23 +338,24 @@ def run_ours(a, rank, world, local_rank):
     NB = 4 if nq <= 20000 else 1
     q_host = [torch.from_numpy(pkg.datagen.make(a.data, nq, a.d, 2 + 1000 * rank + b)).pin_memory() for b in range(NB)]
     q_dev = [q.cuda(non_blocking=True) for q in q_host]
-    out_dev = [torch.empty((nq, a.k, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]   # Neighbour_api[nq][k]
+    NOUT = 4   # answers of 4 consecutive steps may be in flight (search i+1..i+3 while the gather of step i runs)
+    out_dev = [torch.empty((nq, a.k, 16), dtype=torch.uint8, device="cuda") for _ in range(NOUT)]   # Neighbour_api[nq][k]
     cnt_dev = torch.empty((nq,), dtype=torch.int32, device="cuda")
     same_shards = (not a.strong) or a.nq % world == 0
-    gather_dev = [torch.empty((world * nq, a.k, 16), dtype=torch.uint8, device="cuda") for _ in range(2)] if multi and same_shards else None
+    gather_dev = [torch.empty((world * nq, a.k, 16), dtype=torch.uint8, device="cuda") for _ in range(NOUT)] if multi and same_shards else None
     torch.cuda.synchronize()
     # a dedicated (non-default) torch stream: the library's kernels and torch's events go through it, so
     # torch.cuda.Event brackets exactly the launches of the timed region; the all-gathers run on a second stream
     stream = torch.cuda.Stream(device=dev)
-    gstream = torch.cuda.Stream(device=dev)
+    gstream = torch.cuda.Stream(device=dev, priority=-1)   # the gather's few CTAs go first when SM slots free up
     torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
-    ev_gath = [torch.cuda.Event() for _ in range(2)]
+    ev_gath = [torch.cuda.Event() for _ in range(NOUT)]
 
     def step_device(i, sync=False):
-        b = i & 1
-        if gather_dev is not None and i >= 2:
-            stream.wait_event(ev_gath[b])          # the all-gather that read out_dev[b] two steps ago has finished
+        b = i % NOUT
+        if gather_dev is not None and i >= NOUT:
+            stream.wait_event(ev_gath[b])          # the all-gather that read out_dev[b] NOUT steps ago has finished
         ms = h.search_device(q_dev[i % NB].data_ptr(), nq, a.k, a.ef, out_dev[b].data_ptr(), cnt_dev.data_ptr(), sync=sync)
         if gather_dev is not None:                 # ncclAllGather of step i's answers, overlapped with step i+1's search
             h.stream_wait_last(gstream.cuda_stream)
@@ -472,7 +473,8 @@ def run_ours(a, rank, world, local_rank):
     barrier()
     per_rank_s = time.perf_counter() - t0
     note('per-rank e2e done')
-    # (2) N > 1: ONE call on rank 0's handle, the library shards the batch over all the box's GPUs
+    # (2) N > 1: ONE process (rank 0) drives all the box's GPUs through its handle: hnsw_b200_replicate, then the same
+    # submit / wait pipeline, every batch sharded over the N GPUs by the library
     one_call_s = None
     if multi:
         big = None
@@ -482,8 +484,24 @@ def run_ours(a, rank, world, local_rank):
             h.replicate(list(range(world)))       # copies on the other GPUs, NCCL inside this process
             big = [torch.from_numpy(pkg.datagen.make(a.data, total_per_step, a.d, 9000 + b)).pin_memory().numpy()
                    for b in range(2 if total_per_step <= 200000 else 1)]
-        one_call_s = timed(lambda i: h.search_flat(big[i % len(big)], a.k, a.ef, with_internal=False, with_pid=False)
-                           if rank == 0 else None, a.steps, a.warmup, bar=host_barrier)
+
+        def pipelined_big(steps):
+            if rank != 0:
+                return
+            prev = None
+            for i in range(steps):
+                t = h.submit_flat(big[i % len(big)], a.k, a.ef, with_internal=False, with_pid=False)
+                if prev is not None:
+                    h.wait_flat(prev)
+                prev = t
+            h.wait_flat(prev)
+
+        pipelined_big(a.warmup)
+        host_barrier()
+        t0 = time.perf_counter()
+        pipelined_big(a.steps)
+        host_barrier()
+        one_call_s = time.perf_counter() - t0
         if rank == 0:
             h.replicate([dev])
         host_barrier()
@@ -525,8 +543,8 @@ def run_ours(a, rank, world, local_rank):
     traffic, traffic_src = committed_traffic(a)
     e2e = {"value": e2e_v, "unit": "queries/s", "h2d_bytes_per_step": total_per_step * a.d * 4,
            "d2h_bytes_per_step": total_per_step * a.k * 16 + total_per_step * 4,
-           "call": ("one hnsw_b200_search_flat call on rank 0's handle after hnsw_b200_replicate: the library shards the "
-                    f"batch of {total_per_step} queries over {world} GPUs" if multi else
+           "call": ("ONE process: rank 0's handle after hnsw_b200_replicate, hnsw_b200_search_flat_submit / _wait with two batches "
+                    f"in flight, the library shards every batch of {total_per_step} queries over the {world} GPUs" if multi else
                     "hnsw_b200_search_flat_submit / _wait, one host thread, batch i+1 submitted before batch i is collected "
                     "(two batches in flight); pinned host buffers read and written by the kernel (zero-copy)"),
            "host_threads": 1,

@@ -536,37 +536,30 @@ int hnsw_b200_search_flat(const void* h, const void* queries, uint64_t nq, uint6
 
 // Submit / wait: the same search with the call split in two, so that one host thread keeps several batches in flight
 // (batch i+1 is enqueued before batch i's answers are collected).  Unfiltered, one device.
-int64_t hnsw_b200_search_flat_submit(const void* h, const void* queries, uint64_t nq, uint64_t dim, uint64_t knbn,
-                                     uint64_t ef_search, uint64_t* out_ids, float* out_dist, uint32_t* out_internal,
-                                     int32_t* out_pid, int32_t* out_counts) {
-  HB_HS(h);
-  if (!queries || !out_ids || !out_dist || !out_counts || knbn == 0 || nq == 0) return set_err("bad argument");
-  const int ci = ix->acquire_ctx();
-  int r = ix->search_host_begin(ci, queries, nullptr, nq, (int)dim, knbn, ef_search, nullptr);
+// one device's share of a submitted batch: enqueue on a leased context of `rx`, remember where to unpack to
+static int submit_on(Index* rx, int* ctx_out, const void* queries, uint64_t nq, uint64_t dim, uint64_t knbn, uint64_t ef_search,
+                     uint64_t* out_ids, float* out_dist, uint32_t* out_internal, int32_t* out_pid, int32_t* out_counts) {
+  const int ci = rx->acquire_ctx();
+  int r = rx->search_host_begin(ci, queries, nullptr, nq, (int)dim, knbn, ef_search, nullptr);
   if (r) {
-    ix->release_ctx(ci);
-    return pass(ix, r);
+    rx->release_ctx(ci);
+    return r;
   }
-  Index::SearchCtx::Pending& p = ix->ctx(ci).pend;
+  Index::SearchCtx::Pending& p = rx->ctx(ci).pend;
   p.u_ids = out_ids;
   p.u_dist = out_dist;
   p.u_internal = out_internal;
   p.u_pid = out_pid;
   p.u_counts = out_counts;
-  ix->pending_.fetch_add(1);
-  return ci;
+  *ctx_out = ci;
+  return 0;
 }
-
-int hnsw_b200_search_flat_wait(const void* h, int64_t ticket) {
-  if (!h) return set_err("NULL handle");
-  Index* ix = ((const AnyApi*)h)->ix;  // no lock: a writer holding the index exclusively is waiting for this very call
-  if (ticket < 0 || ticket >= Index::NCTX) return set_err("bad ticket");
-  const int ci = (int)ticket;
+static int wait_on(Index* rx, int ci) {
   const NeighbourOut* tmp = nullptr;
   const int32_t* cnts = nullptr;
-  int r = ix->search_host_finish(ci, &tmp, &cnts);
+  int r = rx->search_host_finish(ci, &tmp, &cnts);
   if (!r) {
-    const Index::SearchCtx::Pending& p = ix->ctx(ci).pend;
+    const Index::SearchCtx::Pending& p = rx->ctx(ci).pend;
     memcpy(p.u_counts, cnts, p.nq * sizeof(int32_t));
     const uint64_t tot = p.nq * p.k;
     for (uint64_t s = 0; s < tot; ++s) p.u_ids[s] = tmp[s].origin;
@@ -576,13 +569,61 @@ int hnsw_b200_search_flat_wait(const void* h, int64_t ticket) {
     if (p.u_pid)
       for (uint64_t s = 0; s < tot; ++s) {
         const uint32_t it = tmp[s].internal;
-        p.u_pid[2 * s] = it != hb::INVALID_ID ? (int32_t)ix->h_level[it] : -1;
-        p.u_pid[2 * s + 1] = it != hb::INVALID_ID ? ix->h_rank[it] : -1;
+        p.u_pid[2 * s] = it != hb::INVALID_ID ? (int32_t)rx->h_level[it] : -1;
+        p.u_pid[2 * s + 1] = it != hb::INVALID_ID ? rx->h_rank[it] : -1;
       }
-  } else {
-    g_err = ix->err();
   }
-  ix->release_ctx(ci);
+  rx->release_ctx(ci);
+  return r;
+}
+
+// Submit / wait: the same search with the call split in two, so that one host thread keeps several batches in flight
+// (batch i+1 is enqueued before batch i's answers are collected).  Unfiltered.  With replicas (hnsw_b200_replicate) the
+// batch is sharded like a search_flat call: every device gets its contiguous share enqueued at submit time.
+int64_t hnsw_b200_search_flat_submit(const void* h, const void* queries, uint64_t nq, uint64_t dim, uint64_t knbn,
+                                     uint64_t ef_search, uint64_t* out_ids, float* out_dist, uint32_t* out_internal,
+                                     int32_t* out_pid, int32_t* out_counts) {
+  HB_HS(h);
+  if (!queries || !out_ids || !out_dist || !out_counts || knbn == 0 || nq == 0) return set_err("bad argument");
+  Index::Ticket t;
+  const size_t qrow = (size_t)dim * ix->es;
+  int r = 0;
+  if (use_shards(ix, nq)) {
+    r = ix->for_each_shard_inline(nq, [&](Index* rx, size_t first, size_t count) {
+      int ci = -1;
+      int rr = submit_on(rx, &ci, (const char*)queries + first * qrow, count, dim, knbn, ef_search, out_ids + first * knbn,
+                         out_dist + first * knbn, out_internal ? out_internal + first * knbn : nullptr,
+                         out_pid ? out_pid + 2 * first * knbn : nullptr, out_counts + first);
+      if (!rr) t.parts.push_back({rx, ci});
+      return rr;
+    });
+  } else {
+    int ci = -1;
+    r = submit_on(ix, &ci, queries, nq, dim, knbn, ef_search, out_ids, out_dist, out_internal, out_pid, out_counts);
+    if (!r) t.parts.push_back({ix, ci});
+  }
+  if (r) {
+    for (auto& pr : t.parts) wait_on(pr.first, pr.second);  // collect what was enqueued before the failure
+    return pass(ix, r);
+  }
+  ix->pending_.fetch_add(1);
+  return ix->park_ticket(std::move(t));
+}
+
+int hnsw_b200_search_flat_wait(const void* h, int64_t ticket) {
+  if (!h) return set_err("NULL handle");
+  Index* ix = ((const AnyApi*)h)->ix;  // no lock: a writer holding the index exclusively is waiting for this very call
+  hb::DeviceRestore keep;
+  Index::Ticket t;
+  if (!ix->take_ticket(ticket, t)) return set_err("bad ticket");
+  int r = 0;
+  for (auto& pr : t.parts) {
+    int rr = wait_on(pr.first, pr.second);
+    if (rr && !r) {
+      r = rr;
+      g_err = pr.first->err();
+    }
+  }
   ix->pending_.fetch_sub(1);
   return r;
 }

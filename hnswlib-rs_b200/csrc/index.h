@@ -141,6 +141,14 @@ class Index {
   int replicate(int ndev, const int* devices);
   size_t replica_count() const { return replicas_.size(); }
   int for_each_shard(size_t nq, const std::function<int(Index*, size_t, size_t)>& run);
+  // same shards, visited one after the other on the calling thread (asynchronous enqueues: submit)
+  int for_each_shard_inline(size_t nq, const std::function<int(Index*, size_t, size_t)>& run);
+  // outstanding submit tickets: (index, context) per device
+  struct Ticket {
+    std::vector<std::pair<Index*, int>> parts;
+  };
+  int64_t park_ticket(Ticket&& t);
+  bool take_ticket(int64_t id, Ticket& out);
   void drop_replicas();
   static int nccl_unique_id(unsigned char* out128);
   int nccl_init(int nranks, int rank, const unsigned char* id128);
@@ -262,6 +270,9 @@ class Index {
                     NeighbourOut* d_out, int32_t* d_counts, bool sync, float* kernel_ms);
   std::mutex ctx_mu_;
   std::condition_variable ctx_cv_;
+  std::mutex ticket_mu_, shard_mu_;
+  std::map<int64_t, Ticket> tickets_;
+  int64_t next_ticket_ = 0;
   int last_async_ = -1;
   unsigned ctx_rr_ = 0;        // round robin of the asynchronous device-resident launches
   std::mutex occ_mu_;

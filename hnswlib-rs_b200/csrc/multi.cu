@@ -222,8 +222,43 @@ int Index::replicate(int ndev, const int* devices) {
 }
 
 // Contiguous shards, one per device; shard 0 runs on the calling thread.  `run` is called as run(index, first, count).
+int64_t Index::park_ticket(Ticket&& t) {
+  std::lock_guard<std::mutex> lk(ticket_mu_);
+  const int64_t id = next_ticket_++;
+  tickets_[id] = std::move(t);
+  return id;
+}
+bool Index::take_ticket(int64_t id, Ticket& out) {
+  std::lock_guard<std::mutex> lk(ticket_mu_);
+  auto it = tickets_.find(id);
+  if (it == tickets_.end()) return false;
+  out = std::move(it->second);
+  tickets_.erase(it);
+  return true;
+}
+
+int Index::for_each_shard_inline(size_t nq, const std::function<int(Index*, size_t, size_t)>& run) {
+  DeviceRestore keep;
+  std::lock_guard<std::mutex> one(shard_mu_);
+  if (replicas_stale_) {
+    int r = broadcast_to_replicas();
+    if (r) return r;
+  }
+  const size_t ndev = replicas_.size() + 1;
+  const size_t per = (nq + ndev - 1) / ndev;
+  for (size_t i = 0; i < ndev; ++i) {
+    const size_t first = std::min(nq, i * per), count = std::min(nq, (i + 1) * per) - first;
+    if (!count) continue;
+    Index* rx = i == 0 ? this : replicas_[i - 1].get();
+    int r = run(rx, first, count);
+    if (r) return i == 0 ? r : fail("device " + std::to_string(rx->device) + ": " + rx->err());
+  }
+  return 0;
+}
+
 int Index::for_each_shard(size_t nq, const std::function<int(Index*, size_t, size_t)>& run) {
   DeviceRestore keep;
+  std::lock_guard<std::mutex> one(shard_mu_);  // one sharded call at a time: the workers hold one job each
   if (replicas_stale_) {
     int r = broadcast_to_replicas();
     if (r) return r;

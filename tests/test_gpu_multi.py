@@ -96,6 +96,12 @@ def test_replicated_search_equals_one_gpu(pkg, po):
         assert np.array_equal(a, b)
     for a, b in zip(want_f, h.search_flat(Q, 10, 64, filter=np.arange(0, 20000, 3, dtype=np.uint64))):
         assert np.array_equal(a, b)
+    # submit / wait shards too: two batches in flight over all the devices
+    t1 = h.submit_flat(Q, 10, 64)
+    t2 = h.submit_flat(Q[::-1].copy(), 10, 64)
+    for a, b in zip(want, h.wait_flat(t1)):
+        assert np.array_equal(a, b)
+    assert np.array_equal(h.wait_flat(t2)[2], want[2][::-1])
     par = h.parallel_search([q for q in Q], 10, 64)   # the reference's entry point, row pointers
     assert [[x.d_id for x in nb] for nb in par] == [want[0][i, :want[4][i]].tolist() for i in range(len(Q))]
     # inserting makes the copies stale; the next sharded search re-broadcasts first

@@ -27,6 +27,7 @@ namespace hb {
 struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*);
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*);  // may be null (NCCL < 2.17)
   ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*);
   ncclResult_t (*CommDestroy)(ncclComm_t);
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
@@ -65,6 +66,7 @@ static NcclApi& nccl() {
     HB_SYM(GroupEnd, "ncclGroupEnd")
     HB_SYM(GetErrorString, "ncclGetErrorString")
 #undef HB_SYM
+    api.CommInitRankConfig = reinterpret_cast<decltype(api.CommInitRankConfig)>(dlsym(h, "ncclCommInitRankConfig"));
     api.ok = true;
   });
   return api;
@@ -304,7 +306,16 @@ int Index::nccl_init(int nranks, int rank, const unsigned char* id128) {
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   ncclComm_t c;
-  HB_NCCL(nc.CommInitRank(&c, nranks, id, rank));
+  if (nc.CommInitRankConfig) {
+    // the gathers of this communicator run next to search kernels that fill every SM: keep them to a few CTAs, so that a
+    // gather waiting for its peers does not park thousands of threads
+    ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+    cfg.minCTAs = 1;
+    cfg.maxCTAs = 2;
+    HB_NCCL(nc.CommInitRankConfig(&c, nranks, id, rank, &cfg));
+  } else {
+    HB_NCCL(nc.CommInitRank(&c, nranks, id, rank));
+  }
   comm_ = c;
   nranks_ = nranks;
   rank_ = rank;

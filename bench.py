@@ -16,9 +16,9 @@ metric is quoted on:
   value      queries/s, inputs resident in HBM, K launches timed with CUDA events on the launch stream
   e2e        the same metric through the C-ABI call a user makes with HOST buffers, H2D of the queries and D2H of the
              answers inside the timed region: hnsw_b200_search_flat_submit / _wait with two batches in flight from one
-             host thread (e2e.sequential: one hnsw_b200_search_flat call at a time); at N > 1 ONE search_flat call on
-             rank 0's handle after hnsw_b200_replicate, the library sharding the batch over the N GPUs (e2e.per_rank:
-             every rank pipelining its own shard).  e2e.row_pointers (N = 1): the reference's own entry point
+             host thread, per rank (e2e.sequential: one hnsw_b200_search_flat call at a time; e2e.one_process at N > 1: ONE
+             process, rank 0's handle after hnsw_b200_replicate, the library sharding every batch over the N GPUs).
+             e2e.row_pointers (N = 1): the reference's own entry point
              parallel_search_neighbours_f32 with pageable row pointers and malloc'ed answers
   roofline   algorithmic bytes (E*d*4 + A*4 + d*4 + k*16 per query, E/A counted by the kernel itself and
              equal to the oracle's counters, tests/test_gpu_search.py) / kernel time vs measured HBM peak
@@ -532,7 +532,8 @@ def run_ours(a, rank, world, local_rank):
     value = total_q / (dev_ms / 1e3)
     e2e_per_rank = total_q / (per_rank_ms / 1e3)
     e2e_seq = total_q / (seq_ms / 1e3)
-    e2e_v = total_q / (one_call_ms / 1e3) if multi else e2e_per_rank
+    e2e_v = e2e_per_rank     # same definition at every N: each rank pipelines its own shard through submit / wait
+    e2e_one = total_q / (one_call_ms / 1e3) if multi else None
 
     if rank != 0:
         return
@@ -543,15 +544,16 @@ def run_ours(a, rank, world, local_rank):
     traffic, traffic_src = committed_traffic(a)
     e2e = {"value": e2e_v, "unit": "queries/s", "h2d_bytes_per_step": total_per_step * a.d * 4,
            "d2h_bytes_per_step": total_per_step * a.k * 16 + total_per_step * 4,
-           "call": ("ONE process: rank 0's handle after hnsw_b200_replicate, hnsw_b200_search_flat_submit / _wait with two batches "
-                    f"in flight, the library shards every batch of {total_per_step} queries over the {world} GPUs" if multi else
-                    "hnsw_b200_search_flat_submit / _wait, one host thread, batch i+1 submitted before batch i is collected "
-                    "(two batches in flight); pinned host buffers read and written by the kernel (zero-copy)"),
+           "call": ("hnsw_b200_search_flat_submit / _wait, one host thread" + (" per rank" if multi else "") + ", batch i+1 "
+                    "submitted before batch i is collected (two batches in flight); pinned host buffers read and written by the "
+                    "kernel (zero-copy)"),
            "host_threads": 1,
-           "per_rank": {"value": e2e_per_rank, "unit": "queries/s",
-                        "call": "every rank: hnsw_b200_search_flat_submit / _wait on its own shard, two batches in flight"},
            "sequential": {"value": e2e_seq, "unit": "queries/s",
                           "call": "every rank: one hnsw_b200_search_flat call at a time (no batches in flight together)"}}
+    if multi:
+        e2e["one_process"] = {"value": e2e_one, "unit": "queries/s",
+                              "call": "ONE process: rank 0's handle after hnsw_b200_replicate, the same submit / wait pipeline, the "
+                                      f"library shards every batch of {total_per_step} queries over the {world} GPUs"}
     if rowptr_s is not None:
         e2e["row_pointers"] = {"value": a.steps * nq / rowptr_s, "unit": "queries/s",
                                "call": f"parallel_search_neighbours_f32: {nq} pageable row pointers in, malloc'ed "

@@ -617,11 +617,13 @@ int hnsw_b200_search_flat_wait(const void* h, int64_t ticket) {
   Index::Ticket t;
   if (!ix->take_ticket(ticket, t)) return set_err("bad ticket");
   int r = 0;
-  for (auto& pr : t.parts) {
-    int rr = wait_on(pr.first, pr.second);
-    if (rr && !r) {
-      r = rr;
-      g_err = pr.first->err();
+  if (t.parts.size() > 1) {  // sharded batch: every device's part is collected and unpacked by that device's worker thread
+    r = ix->finish_parts(t.parts, [](Index* rx, int ci) { return wait_on(rx, ci); });
+    if (r) g_err = ix->err();
+  } else {
+    for (auto& pr : t.parts) {
+      r = wait_on(pr.first, pr.second);
+      if (r) g_err = pr.first->err();
     }
   }
   ix->pending_.fetch_sub(1);

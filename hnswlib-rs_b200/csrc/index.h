@@ -147,6 +147,7 @@ class Index {
   struct Ticket {
     std::vector<std::pair<Index*, int>> parts;
   };
+  int finish_parts(const std::vector<std::pair<Index*, int>>& parts, const std::function<int(Index*, int)>& fn);
   int64_t park_ticket(Ticket&& t);
   bool take_ticket(int64_t id, Ticket& out);
   void drop_replicas();

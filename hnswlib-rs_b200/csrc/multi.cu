@@ -239,6 +239,35 @@ bool Index::take_ticket(int64_t id, Ticket& out) {
   return true;
 }
 
+// the parts of a submitted batch finished in parallel: part (replica i, ctx) on replica i's worker thread, the root's part on
+// the calling thread
+int Index::finish_parts(const std::vector<std::pair<Index*, int>>& parts, const std::function<int(Index*, int)>& fn) {
+  DeviceRestore keep;
+  std::lock_guard<std::mutex> one(shard_mu_);
+  std::vector<int> rc(parts.size(), 0);
+  std::vector<Worker*> used;
+  int own = -1;
+  for (size_t k = 0; k < parts.size(); ++k) {
+    Worker* w = nullptr;
+    for (size_t i = 0; i < replicas_.size(); ++i)
+      if (replicas_[i].get() == parts[k].first) w = workers_[i].get();
+    if (!w) {
+      own = (int)k;
+      continue;
+    }
+    int* out = &rc[k];
+    Index* rx = parts[k].first;
+    const int ci = parts[k].second;
+    w->submit([=, &fn] { *out = fn(rx, ci); });
+    used.push_back(w);
+  }
+  if (own >= 0) rc[own] = fn(parts[own].first, parts[own].second);
+  for (Worker* w : used) w->wait();
+  for (size_t k = 0; k < parts.size(); ++k)
+    if (rc[k]) return parts[k].first == this ? rc[k] : fail("device " + std::to_string(parts[k].first->device) + ": " + parts[k].first->err());
+  return 0;
+}
+
 int Index::for_each_shard_inline(size_t nq, const std::function<int(Index*, size_t, size_t)>& run) {
   DeviceRestore keep;
   std::lock_guard<std::mutex> one(shard_mu_);

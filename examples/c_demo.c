@@ -40,6 +40,19 @@ int main(void) {
   const Vec_api_Neighbourhood_api* v = parallel_search_neighbours_f32(h, 3, D, rows, 4, 32);
   ok = ok && v && v->len == 3 && v->ptr[2].neighbours[0].id == 1002;
   hnsw_b200_free_vec_api(v);
+  /* extensions: two batches in flight from this one thread (submit / wait), the replicas call (a no-op on one device) */
+  {
+    int dev0 = 0;
+    uint64_t out_ids[2][8 * 4];
+    float out_d[2][8 * 4];
+    int32_t cnt[2][8];
+    int64_t t0, t1;
+    ok = ok && hnsw_b200_replicate((void*)h, 1, &dev0) == 0 && hnsw_b200_replica_count(h) == 0;
+    t0 = hnsw_b200_search_flat_submit(h, data, 8, D, 4, 32, out_ids[0], out_d[0], NULL, NULL, cnt[0]);
+    t1 = hnsw_b200_search_flat_submit(h, data + 8 * D, 8, D, 4, 32, out_ids[1], out_d[1], NULL, NULL, cnt[1]);
+    ok = ok && t0 >= 0 && t1 >= 0 && hnsw_b200_search_flat_wait(h, t0) == 0 && hnsw_b200_search_flat_wait(h, t1) == 0;
+    ok = ok && cnt[0][3] == 4 && out_ids[0][3 * 4] == 1003 && out_ids[1][0] == 1008 && out_d[1][0] == 0.0f;
+  }
   drop_hnsw_f32(h);
   free(data);
   free(rows);

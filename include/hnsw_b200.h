@@ -251,7 +251,7 @@ int hnsw_b200_search_flat(const void* h, const void* queries, uint64_t nq, uint6
  * flight: submit enqueues the batch and returns a ticket (>= 0; < 0 on error) at once, wait blocks until its answers
  * are in the arrays given to submit.  Up to 4 batches may be in flight per handle (a fifth submit blocks); the query and
  * output arrays must stay valid and untouched until wait returns; calls that change the index wait for outstanding
- * tickets.  Batches in flight together overlap on the GPU (see hnsw_b200_search_device). */
+ * tickets (so a thread must collect its own tickets before it inserts).  Batches in flight together overlap on the GPU (see hnsw_b200_search_device). */
 int64_t hnsw_b200_search_flat_submit(const void* h, const void* queries, uint64_t nq, uint64_t dim, uint64_t knbn,
                                      uint64_t ef_search, uint64_t* out_ids, float* out_dist, uint32_t* out_internal,
                                      int32_t* out_pid, int32_t* out_counts);

@@ -49,9 +49,9 @@ int main(void) {
     int64_t t0, t1;
     ok = ok && hnsw_b200_replicate((void*)h, 1, &dev0) == 0 && hnsw_b200_replica_count(h) == 0;
     t0 = hnsw_b200_search_flat_submit(h, data, 8, D, 4, 32, out_ids[0], out_d[0], NULL, NULL, cnt[0]);
-    t1 = hnsw_b200_search_flat_submit(h, data + 8 * D, 8, D, 4, 32, out_ids[1], out_d[1], NULL, NULL, cnt[1]);
+    t1 = hnsw_b200_search_flat_submit(h, data, 8, D, 4, 32, out_ids[1], out_d[1], NULL, NULL, cnt[1]);
     ok = ok && t0 >= 0 && t1 >= 0 && hnsw_b200_search_flat_wait(h, t0) == 0 && hnsw_b200_search_flat_wait(h, t1) == 0;
-    ok = ok && cnt[0][3] == 4 && out_ids[0][3 * 4] == 1003 && out_ids[1][0] == 1008 && out_d[1][0] == 0.0f;
+    ok = ok && cnt[0][7] == 4 && out_ids[0][7 * 4] == 1007 && out_d[0][7 * 4] == 0.0f && out_ids[1][2 * 4] == 1002;
   }
   drop_hnsw_f32(h);
   free(data);

@@ -315,3 +315,24 @@ def test_tie_mode_std_equals_default_without_ties(pkg, po):
     b = h.search_flat(Q, 10, 48)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_filtered_search_on_tie_heavy_metric_matches_oracle(pkg, po):
+    """the filtered stop / retain rule compares distances only (hnsw.rs:981).  With Hamming data, where a popped
+    candidate often TIES with W's farthest, a (distance, id) comparison would run the retain pass where the reference does
+    not; kernel and oracle must agree on ids, distances and counts with both filter forms, also at small ef."""
+    n, d = 2000, 32
+    rng = np.random.default_rng(11)
+    X = rng.integers(0, 3, (n, d)).astype(np.uint8)
+    Q = rng.integers(0, 3, (120, d)).astype(np.uint8)
+    o = po.Oracle(8, n, 16, 64, "DistHamming", d, dtype=np.uint8, mode=po.MODE_DET, order=po.ORDER_GPU)
+    o.insert_batch(X)
+    lv, rk, og = o.export_points()
+    h = pkg.Hnsw(8, n, 16, 64, "DistHamming", dtype=np.uint8)
+    h.import_graph(X, og, lv, o.entry, oracle_layers(o))
+    for allow, k, ef in ((np.arange(0, n, 3), 10, 32), (np.arange(5, n, 17), 5, 8), (np.arange(0, n, 2), 10, 10)):
+        oo, od, oi, _, oc = o.search_batch(Q, k, ef, filter_ids=allow)
+        go, gd, gi, _, gc = h.search_flat(Q, k, ef, filter=allow)
+        assert np.array_equal(gc, oc), (k, ef)
+        assert np.array_equal(gi, oi), (k, ef)
+        assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))

@@ -338,11 +338,16 @@ def run_ours(a, rank, world, local_rank):
     NB = 4 if nq <= 20000 else 1
     q_host = [torch.from_numpy(pkg.datagen.make(a.data, nq, a.d, 2 + 1000 * rank + b)).pin_memory() for b in range(NB)]
     q_dev = [q.cuda(non_blocking=True) for q in q_host]
-    NOUT = 4   # answers of 4 consecutive steps may be in flight (search i+1..i+3 while the gather of step i runs)
-    out_dev = [torch.empty((nq, a.k, 16), dtype=torch.uint8, device="cuda") for _ in range(NOUT)]   # Neighbour_api[nq][k]
+    # Answers live in groups of GSTEP consecutive steps (one contiguous buffer per group, NGRP groups rotating): the answers of
+    # a whole group are all-gathered by ONE collective on a second stream while the next groups search, so the GPUs
+    # rendezvous once per GSTEP steps instead of every step.
+    GSTEP, NGRP = 2, 3
+    out_grp = [torch.empty((GSTEP, nq, a.k, 16), dtype=torch.uint8, device="cuda") for _ in range(NGRP)]   # Neighbour_api[nq][k] x GSTEP
+    out_dev = [out_grp[0][0]]                       # kernel-only timings and the single-GPU path write here
     cnt_dev = torch.empty((nq,), dtype=torch.int32, device="cuda")
     same_shards = (not a.strong) or a.nq % world == 0
-    gather_dev = [torch.empty((world * nq, a.k, 16), dtype=torch.uint8, device="cuda") for _ in range(NOUT)] if multi and same_shards else None
+    gather_grp = [torch.empty((world, GSTEP, nq, a.k, 16), dtype=torch.uint8, device="cuda") for _ in range(NGRP)] if multi and same_shards else None
+    gather_dev = gather_grp
     torch.cuda.synchronize()
     # a dedicated (non-default) torch stream: the library's kernels and torch's events go through it, so
     # torch.cuda.Event brackets exactly the launches of the timed region; the all-gathers run on a second stream
@@ -350,22 +355,31 @@ def run_ours(a, rank, world, local_rank):
     gstream = torch.cuda.Stream(device=dev, priority=-1)   # the gather's few CTAs go first when SM slots free up
     torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
-    ev_gath = [torch.cuda.Event() for _ in range(NOUT)]
+    ev_gath = [torch.cuda.Event() for _ in range(NGRP)]
+    open_group = [None]                            # group with launches not gathered yet
+
+    def gather_group(g):
+        h.nccl_allgather(out_grp[g].data_ptr(), gather_grp[g].data_ptr(), GSTEP * nq * a.k * 16, gstream.cuda_stream)
+        ev_gath[g].record(gstream)
+        open_group[0] = None
 
     def step_device(i, sync=False):
-        b = i % NOUT
-        if gather_dev is not None and i >= NOUT:
-            stream.wait_event(ev_gath[b])          # the all-gather that read out_dev[b] NOUT steps ago has finished
-        ms = h.search_device(q_dev[i % NB].data_ptr(), nq, a.k, a.ef, out_dev[b].data_ptr(), cnt_dev.data_ptr(), sync=sync)
-        if gather_dev is not None:                 # ncclAllGather of step i's answers, overlapped with step i+1's search
-            h.stream_wait_last(gstream.cuda_stream)
-            h.nccl_allgather(out_dev[b].data_ptr(), gather_dev[b].data_ptr(), nq * a.k * 16, gstream.cuda_stream)
-            ev_gath[b].record(gstream)
+        g, j = (i // GSTEP) % NGRP, i % GSTEP
+        if gather_grp is not None and j == 0 and i >= GSTEP * NGRP:
+            stream.wait_event(ev_gath[g])          # the all-gather that read this group NGRP groups ago has finished
+        ms = h.search_device(q_dev[i % NB].data_ptr(), nq, a.k, a.ef, out_grp[g][j].data_ptr(), cnt_dev.data_ptr(), sync=sync)
+        if gather_grp is not None:
+            h.stream_wait_last(gstream.cuda_stream)   # the gather stream waits for every launch of the group
+            open_group[0] = g
+            if j == GSTEP - 1:
+                gather_group(g)                    # ncclAllGather of the group's answers, overlapped with the next searches
         return ms
 
     def drain():
+        if gather_grp is not None and open_group[0] is not None:
+            gather_group(open_group[0])            # a group left half-filled by an odd number of steps
         h.join()                                   # the launch stream waits for the launches in flight on the contexts
-        if gather_dev is not None:
+        if gather_grp is not None:
             stream.wait_stream(gstream)
 
     note('buffers ready')
@@ -570,8 +584,9 @@ def run_ours(a, rank, world, local_rank):
                   f"{'exceeds' if a.n * (a.d * 4 + a.M * 8) > 126e6 else 'FITS IN'} the 126 MB L2; {NB} query batch(es) rotated",
             "overlap": "device-resident launches are asynchronous and alternate between two search contexts (streams, visited "
                        "tables, work counters) of the index: step i+1 starts while step i's last queries finish",
-            "parallelism": (f"query-sharded x{world}, index replicated (ncclBroadcast inside the library), answers ncclAllGather "
-                            "on a second stream, overlapped with the next step; replicas checked against rank 0") if multi else "1 GPU",
+            "parallelism": (f"query-sharded x{world}, index replicated (ncclBroadcast inside the library), answers of every 2 steps "
+                            "all-gathered by one ncclAllGather on a second stream, overlapped with the next steps; replicas checked "
+                            "against rank 0") if multi else "1 GPU",
         },
         "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

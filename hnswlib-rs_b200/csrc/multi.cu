@@ -214,7 +214,11 @@ int Index::replicate(int ndev, const int* devices) {
   }
   replica_devices_.assign(devices, devices + ndev);
   std::vector<ncclComm_t> cs(ndev);
-  HB_NCCL(nc.CommInitAll(cs.data(), ndev, devices));
+  const ncclResult_t ir = nc.CommInitAll(cs.data(), ndev, devices);
+  if (ir != ncclSuccess) {
+    drop_replicas();  // no half-made replica set: the handle goes on answering from its own device
+    return fail(std::string("replicate: ncclCommInitAll: ") + nc.GetErrorString(ir));
+  }
   comms_.assign(cs.begin(), cs.end());
   for (int i = 1; i < ndev; ++i) workers_.emplace_back(new Worker());  // NOLINT: owned by workers_
   int r = broadcast_to_replicas();
@@ -223,7 +227,7 @@ int Index::replicate(int ndev, const int* devices) {
   return r;
 }
 
-// Contiguous shards, one per device; shard 0 runs on the calling thread.  `run` is called as run(index, first, count).
+// tickets of submitted batches (hnsw_b200_search_flat_submit / _wait)
 int64_t Index::park_ticket(Ticket&& t) {
   std::lock_guard<std::mutex> lk(ticket_mu_);
   const int64_t id = next_ticket_++;
@@ -287,6 +291,7 @@ int Index::for_each_shard_inline(size_t nq, const std::function<int(Index*, size
   return 0;
 }
 
+// Contiguous shards, one per device; shard 0 runs on the calling thread.  `run` is called as run(index, first, count).
 int Index::for_each_shard(size_t nq, const std::function<int(Index*, size_t, size_t)>& run) {
   DeviceRestore keep;
   std::lock_guard<std::mutex> one(shard_mu_);  // one sharded call at a time: the workers hold one job each
@@ -357,8 +362,12 @@ int Index::nccl_broadcast_index(int root) {
   if (!comm_) return fail("nccl_broadcast_index: call hnsw_b200_nccl_init first");
   if (root < 0 || root >= nranks_) return fail("nccl_broadcast_index: bad root");
   HB_CUDA(cudaSetDevice(device));
-  uint64_t* d_hdr = nullptr;
-  HB_CUDA(cudaMalloc(&d_hdr, 16 * sizeof(uint64_t)));
+  struct DevBuf {  // freed on every return path
+    uint64_t* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+  } hdr;
+  HB_CUDA(cudaMalloc(&hdr.p, 16 * sizeof(uint64_t)));
+  uint64_t* d_hdr = hdr.p;
   uint64_t header[16];
   if (rank_ == root) {
     blob_header(header);
@@ -367,7 +376,6 @@ int Index::nccl_broadcast_index(int root) {
   HB_NCCL(nc.Broadcast(d_hdr, d_hdr, sizeof(header), ncclChar, root, (ncclComm_t)comm_, stream_));
   HB_CUDA(cudaMemcpyAsync(header, d_hdr, sizeof(header), cudaMemcpyDeviceToHost, stream_));
   HB_CUDA(cudaStreamSynchronize(stream_));
-  cudaFree(d_hdr);
   int r;
   if (rank_ != root && (r = blob_alloc(header))) return r;
   for (int b = 0; b < blob_count(); ++b) {

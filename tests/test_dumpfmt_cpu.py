@@ -56,3 +56,43 @@ def test_oracle_graph_roundtrip(tmp_path, pkg, po):
     for p in (0, 17, 499):
         want = [(int(inv[ids[j]]), float(ds[j])) for j in range(int(off[p]), int(off[p + 1]))]
         assert b["lists"][0][int(inv[p])] == want
+
+
+class _DescriptionFFI(__import__("ctypes").Structure):
+    """#[repr(C)] DescriptionFFI, libext.rs:1121-1141 (include/hnsw_b200.h)."""
+    import ctypes as _C
+    _fields_ = [("dumpmode", _C.c_uint8), ("max_nb_connection", _C.c_uint8), ("nb_layer", _C.c_uint8),
+                ("ef", _C.c_size_t), ("nb_point", _C.c_size_t), ("data_dimension", _C.c_size_t),
+                ("distname_len", _C.c_size_t), ("distname", _C.c_void_p),
+                ("t_name_len", _C.c_size_t), ("t_name", _C.c_void_p)]
+
+
+def test_library_reads_description_of_independent_dump(tmp_path, pkg, po):
+    """load_hnsw_description (libext.rs:1170-1232) is host-only: the library's reader against a dump written by the
+    independent writer of oracle/dumpfmt.py, and its refusal of a file that is not a dump."""
+    import ctypes as C
+    import dumpfmt
+    X = pkg.datagen.uniform(300, 9, 4)
+    o = po.Oracle(12, 300, 16, 50, "DistL1", 9)
+    o.insert_batch(X, ids=np.arange(300))
+    lv, rk, og = o.export_points()
+    layers = [o.export_layer(l) for l in range(int(lv.max()) + 1)]
+    base = str(tmp_path / "desc")
+    dumpfmt.write_dump(base, X, og, lv, o.entry, layers, 12, 50, 1 / np.log(12), "DistL1")
+    L = pkg.load_library()
+    path = (base + ".hnsw.graph").encode()
+    dptr = L.load_hnsw_description(len(path), path)
+    assert dptr
+    d = C.cast(dptr, C.POINTER(_DescriptionFFI)).contents
+    assert (d.dumpmode, d.max_nb_connection, d.nb_layer) == (1, 12, 16)
+    assert (d.ef, d.nb_point, d.data_dimension) == (50, 300, 9)
+    assert C.string_at(d.distname, d.distname_len).endswith(b"DistL1")
+    assert C.string_at(d.t_name, d.t_name_len) == b"f32"
+    L.hnsw_b200_free_description(dptr)
+    bad = tmp_path / "bad.hnsw.graph"
+    bad.write_bytes(b"\x00" * 64)
+    p2 = str(bad).encode()
+    assert not L.load_hnsw_description(len(p2), p2)
+    assert L.hnsw_b200_last_error()
+    missing = str(tmp_path / "nope.hnsw.graph").encode()
+    assert not L.load_hnsw_description(len(missing), missing)
